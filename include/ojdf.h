@@ -1,0 +1,119 @@
+/*
+ * ojdf.h -- C ABI of the B200-native per-frame TSDF-fusion hot path.
+ *
+ * The reference (suryanshkumar/online-joint-depthfusion-and-semantic @ a4f9e19) has no
+ * FFI layer: its hot path is ~1500 ATen calls per frame issued from
+ *   modules/extractor.py:24-79   Extractor.forward
+ *   modules/integrator.py:15-126 Integrator.forward
+ *   modules/pipeline.py:137-171  Pipeline._prepare_volume_update
+ * Each entry point below replaces one of those call sites with hand-written sm_100a
+ * kernels.  The host-side mirror of the reference classes (the package's modules/*.py)
+ * binds these symbols with ctypes; INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - every `*_dev` pointer is a DEVICE pointer owned by the caller (torch tensors);
+ *     `*_host` pointers are small HOST arrays read synchronously during the call;
+ *   - fp16 volumes are raw IEEE binary16 arrays, dense row-major (X,Y,Z), z fastest,
+ *     linear index (x*Y + y)*Z + z           (modules/integrator.py:57);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the
+ *     call returns without synchronising;
+ *   - nothing is allocated: scratch comes from a caller-provided workspace;
+ *   - return value 0 = success, OJDF_ERR_* (< 0) = argument error, > 0 = cudaError_t.
+ *   - no torch types, no C++ types, no exceptions cross this boundary.
+ */
+#ifndef OJDF_H
+#define OJDF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OJDF_VERSION 100
+
+#define OJDF_ERR_BADARG (-1)      /* null pointer / non-positive size / P even or > 33 */
+#define OJDF_ERR_WORKSPACE (-2)   /* workspace missing or too small */
+#define OJDF_ERR_TOOLARGE (-3)    /* grid or entry count does not fit 32-bit keys */
+
+int ojdf_version(void);
+/* Human-readable text for a return code of this library. */
+const char *ojdf_error_string(int code);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t ojdf_launch_count(void);
+
+/* ---- a5: Extractor.compute_coordinates (modules/extractor.py:82-120) -----------------
+ * depth (h,w) f32 -> world (h*w,3) f32.  Kinv = intrinsics.float().inverse() (3x3 row
+ * major, computed by the host exactly as the reference does), E = cam->world rows 0..2
+ * (3x4 row major).  Each output is the f32 FMA chain t=fl(a0*b0); t=fma(a1,b1,t); ...
+ * (what the reference's BLAS does at the benchmark shapes). */
+int ojdf_unproject(const float *depth_dev, int h, int w, const float *Kinv_host, const float *E_host,
+                   float *world_dev, void *stream);
+
+/* ---- a4/a6/a7/a8: Extractor.forward (modules/extractor.py:24-79, 309-345, 533-681) ---
+ * One pass per frame: per-ray voxel-space sample points (f64, P = n_points samples at
+ * 1-voxel spacing, index 0 nearest the camera), 8 trilinear corners per sample, gather of
+ * the fp16 TSDF and weight volumes (out-of-grid corners read -0.1 / 0,
+ * modules/extractor.py:663-664), f64 weighted sum in the reference's order -> f32.
+ *
+ *   depth_dev     (h,w) f32, or NULL when world_in_dev is given
+ *   world_in_dev  optional (h*w,3) f32: use these world points instead of unprojecting
+ *                 (parity tests feed the oracle's `pcl` here)
+ *   eye is E[:,3] (modules/extractor.py:57)
+ *   out_vals_dev / out_wts_dev   (N,P) f32   = values['fusion_values' / 'fusion_weights']
+ *   out_world_dev   optional (N,3) f32       = values['pcl']
+ *   out_ray_dev     optional (N,6) f64       = per-ray (centre_voxel xyz, unit direction xyz);
+ *                                              the compact form ojdf_integrate() consumes
+ *   out_points_dev  optional (N,P,3) f64     = values['points']
+ *   out_idx_dev     optional (N,P,8,3) i64   = values['indices']
+ *   out_w_dev       optional (N,P,8) f64     = values['weights']
+ */
+int ojdf_extract(const float *depth_dev, const float *world_in_dev, int h, int w,
+                 const float *Kinv_host, const float *E_host, const double *origin_host, double resolution,
+                 const void *tsdf_dev, const void *wvol_dev, int X, int Y, int Z, int P,
+                 float *out_vals_dev, float *out_wts_dev, float *out_world_dev, double *out_ray_dev,
+                 double *out_points_dev, int64_t *out_idx_dev, double *out_w_dev, void *stream);
+
+/* Bytes of scratch ojdf_integrate*() needs for up to `max_entries` (ray,sample,corner)
+ * entries per call: N*tail*8 for the frame form, M1*8 for the updates form. */
+size_t ojdf_integrate_workspace_bytes(int64_t max_entries);
+/* Put a fresh (or dirty, after a failed call) workspace into its idle state.  Must be
+ * enqueued once before the first ojdf_integrate*() on that workspace. */
+int ojdf_integrate_workspace_init(void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* ---- a13/a14/a15: _prepare_volume_update + Integrator.forward, whole-frame form ------
+ * (modules/pipeline.py:137-171, modules/integrator.py:29-124).  Consumes the extractor's
+ * per-ray record instead of the materialised indices/weights.
+ *   ray_dev         (N,6) f64 from ojdf_extract(out_ray_dev)
+ *   filt_depth_dev  (N) f32: masked depth; rays with 0 are skipped (pipeline.py:143-146)
+ *   est_dev         (N,P) f32 network output; samples 0..tail-1 are integrated after
+ *                   clamping to +-clamp_value (pipeline.py:156-159)
+ *   pix_ids_dev (N) u8 / pix_scores_dev (N) f32: per-pixel label and score, broadcast
+ *                   over the ray's samples (pipeline.py:161-169); used when do_semantics
+ *   volumes are updated IN PLACE.  Per voxel the contributions are summed in fp32 in
+ *   ascending (ray, sample, corner) order -- the reference's CPU index_add_ order -- and
+ *   the semantic "last writer" is the highest entry, so the
+ *   result is deterministic and bit-identical to the single-threaded reference.
+ */
+int ojdf_integrate(const double *ray_dev, const float *filt_depth_dev, const float *est_dev, int64_t N,
+                   int P, int tail, float clamp_value,
+                   void *tsdf_dev, void *wvol_dev, int X, int Y, int Z,
+                   const uint8_t *pix_ids_dev, const float *pix_scores_dev,
+                   uint8_t *ids_vol_dev, void *scores_vol_dev, int do_semantics,
+                   void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* ---- a14/a15 in the reference's own `updates` form (modules/integrator.py:15-126) ------
+ *   values_dev (M1) f32 already clamped, idx_dev (M1,8,3) i64, w_dev (M1,8) f64,
+ *   ids_dev (M1) u8, scores_dev (M1) f32; entry e = m*8 + c.  Same ordering guarantees. */
+int ojdf_integrate_updates(const float *values_dev, const int64_t *idx_dev, const double *w_dev, int64_t M1,
+                           void *tsdf_dev, void *wvol_dev, int X, int Y, int Z,
+                           const uint8_t *ids_dev, const float *scores_dev,
+                           uint8_t *ids_vol_dev, void *scores_vol_dev, int do_semantics,
+                           void *workspace_dev, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OJDF_H */

@@ -1,0 +1,79 @@
+"""ctypes binding of csrc/libojdf.so -- the only way the host side reaches the GPU kernels.
+
+There is deliberately no fallback: if the library is missing or a call fails, this module
+raises.  Signatures mirror include/ojdf.h one to one.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, 'csrc', 'libojdf.so')
+_lib = None
+
+_vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
+
+_SIGNATURES = {
+    'ojdf_version': (C.c_int, []),
+    'ojdf_error_string': (C.c_char_p, [_i]),
+    'ojdf_launch_count': (C.c_uint64, []),
+    'ojdf_unproject': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    'ojdf_extract': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _d, _vp, _vp, _i, _i, _i, _i,
+                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'ojdf_integrate_workspace_bytes': (_sz, [_i64]),
+    'ojdf_integrate_workspace_init': (_i, [_vp, _sz, _vp]),
+    'ojdf_integrate': (_i, [_vp, _vp, _vp, _i64, _i, _i, _f, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i,
+                            _vp, _sz, _vp]),
+    'ojdf_integrate_updates': (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i,
+                                    _vp, _sz, _vp]),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+
+
+class OjdfError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libojdf.so (once).  Raises if it has not been built -- never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise OjdfError('%s is missing: build it with `python -m online_joint_depthfusion_and_semantic_b200.build` '
+                            '(there is no CPU or PyTorch fallback for the fusion hot path)' % SO_PATH)
+        l = C.CDLL(SO_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise OjdfError('libojdf: %s (code %d)' % (lib().ojdf_error_string(code).decode(), code))
+
+
+def ptr(t):
+    """Device (or host) pointer of a contiguous tensor, None -> NULL."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), 'ojdf: tensor must be contiguous'
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise OjdfError('ojdf: the fusion hot path runs on CUDA tensors only (got a %s tensor); '
+                            'there is no CPU fallback' % t.device)
+
+
+def launch_count():
+    return int(lib().ojdf_launch_count())
