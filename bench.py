@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- fused frames/s at 240x320 RGB-D into a 256^3 grid (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one RGB-D frame through the whole per-frame path of BASELINE.json configs[1]:
+AdapNet++ (stage 2, 30 classes) -> softmax/max -> Extractor -> FusionNet_v3 (semantic head on)
+-> Integrator (TSDF + semantics), via the public `Pipeline.fuse(batch, database, device)`.
+Data are synthetic (analytic SDF room, seeded) and the networks are random-init (seed 1911):
+there is no dataset, checkpoint or network in this environment.
+
+Own arm (default): one process per GPU, scenes sharded one-per-rank (4 scenes per rank,
+rotated every frame so the voxel working set exceeds L2), no data-path collective.
+  value  = frames/s with the frame tensors already resident in HBM
+  e2e    = frames/s through the same call with HOST (pinned) frame tensors: H2D of
+           image+depth+mask every step and a D2H read of the step's scalar result
+  roofline = algorithmic bytes of the integrate kernels (817 B per valid ray)
+           / their CUDA-event time, against the measured HBM peak
+  cpu_baseline = the CPU port of the same frame (oracle C for extract/integrate + the same
+           torch modules on CPU for the two networks) on a bounded sample, rank 0, N=1 only
+
+Reference arm (--impl reference): that CPU port, timed on the host cores, same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from online_joint_depthfusion_and_semantic_b200 import _lib  # noqa: E402
+from online_joint_depthfusion_and_semantic_b200.config import fusion_config  # noqa: E402
+from online_joint_depthfusion_and_semantic_b200.synthetic import SyntheticScene  # noqa: E402
+
+H, W, GRID, N_CLASSES = 240, 320, 256, 30
+SCENES_PER_RANK, FRAMES_PER_SCENE = 4, 6
+METRIC = 'fused_frames_per_second_240x320_into_256cube'
+WORKLOAD = 'configs[1]: synthetic Replica-like room, 256^3 grid, 240x320 RGB-D, AdapNet++(stage2,30cls)+FusionNet_v3(sem)+extract+integrate'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+class SceneSet:
+    """`dataset` for modules.database.Database: analytic scenes with GT grids."""
+
+    def __init__(self, scenes, device):
+        self._scenes = {s.name: s for s in scenes}
+        self.scenes = list(self._scenes)
+        self.device = device
+
+    def get_grid(self, name, truncation, semantic_grid):
+        from online_joint_depthfusion_and_semantic_b200.modules.database import Voxelgrid
+        s = self._scenes[name]
+        sdf, lab = s.gt_volumes(device=self.device, truncation=truncation)
+        g = Voxelgrid(s.resolution); g.from_array(sdf, s.bbox)
+        l = Voxelgrid(s.resolution); l.from_array(lab, s.bbox)
+        return (g, l)
+
+
+def build_world(device, rank, h=H, w=W, grid=GRID, scenes_per_rank=SCENES_PER_RANK, frames=FRAMES_PER_SCENE,
+                render_device=None):
+    from online_joint_depthfusion_and_semantic_b200.config import Config
+    from online_joint_depthfusion_and_semantic_b200.modules.database import Database
+    from online_joint_depthfusion_and_semantic_b200.modules.pipeline import Pipeline
+    cfg = fusion_config(h, w, semantics='class30', semantic_strategy='predict', use_semantics=True,
+                        n_classes=N_CLASSES, stage=2, device=str(device))
+    torch.manual_seed(1911)
+    pipe = Pipeline(cfg)
+    gen = torch.Generator().manual_seed(1911)
+    for m in pipe.modules():                       # non-trivial BN statistics, like a trained model
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(0.1 * torch.randn(m.num_features, generator=gen))
+            m.running_var.copy_(0.5 + torch.rand(m.num_features, generator=gen))
+    pipe = pipe.to(device).eval()
+    scenes = [SyntheticScene(name='scene%d_%d' % (rank, i), grid=grid, h=h, w=w, n_frames=frames,
+                             seed=rank * scenes_per_rank + i, intrinsics='pinhole')
+              for i in range(scenes_per_rank)]
+    db = Database(SceneSet(scenes, device), Config(device=device, implementation='efficient', init_value=0.1,
+                                                   semantics='class30', semantic_grid=True))
+    rd = render_device or device
+    host_frames = []
+    for f in range(frames):
+        for s in scenes:                            # scene rotates fastest: consecutive frames hit different volumes
+            b = s.frame(f, device=rd)
+            hb = {k: (v.cpu().pin_memory() if torch.is_tensor(v) and torch.cuda.is_available() else
+                      (v.cpu() if torch.is_tensor(v) else v)) for k, v in b.items()}
+            host_frames.append(hb)
+    return cfg, pipe, db, host_frames
+
+
+_DEVICE_KEYS = ('image', 'tof_depth', 'mask')
+
+
+def to_device_frame(hb, device):
+    """H2D of the per-frame tensors the kernels read; the pose (100 bytes) stays on the host."""
+    out = dict(hb)
+    for k in _DEVICE_KEYS:
+        out[k] = hb[k].to(device, non_blocking=True)
+    return out
+
+
+def h2d_bytes(hb):
+    return int(sum(hb[k].numel() * hb[k].element_size() for k in _DEVICE_KEYS))
+
+
+class ResultTap:
+    """Captures the step's scalar result (mean |tsdf update| of the frame) from Pipeline._fusion."""
+
+    def __init__(self, pipe):
+        self.value = None
+        inner = pipe._fusion
+
+        def tapped(inputs, values):
+            est = inner(inputs, values)
+            self.value = est.abs().mean()
+            return est
+        pipe._fusion = tapped
+
+
+def run_own(args):
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: the own arm needs a CUDA device (no CPU fallback); use --impl reference for the CPU port')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    torch.backends.cudnn.allow_tf32 = False          # the reference computes its convs in fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+    _lib.lib()
+
+    cfg, pipe, db, host_frames = build_world(device, rank)
+    tap = ResultTap(pipe)
+    dev_frames = [to_device_frame(hb, device) for hb in host_frames]
+    torch.cuda.synchronize()
+    nf = len(host_frames)
+
+    def step_resident(i):
+        pipe.fuse(dict(dev_frames[i % nf]), db, device)
+
+    def step_e2e(i):
+        b = to_device_frame(host_frames[i % nf], device)
+        pipe.fuse(b, db, device)
+        return float(tap.value.item())              # D2H read of the step's result (4 bytes) -> also a sync
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, with_clocks=False):
+        with torch.no_grad():
+            for i in range(warmup):
+                fn(i)
+            barrier()
+            sampler = ClockSampler(local) if with_clocks else None
+            if sampler:
+                sampler.__enter__()
+            l0 = _lib.launch_count()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(steps):
+                fn(warmup + i)
+            b.record()
+            barrier()
+            launches = _lib.launch_count() - l0
+            if sampler:
+                sampler.__exit__()
+        ms = torch.tensor([a.elapsed_time(b)], device=device, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), launches, (sampler.summary() if sampler else None)
+
+    # --- value: frames resident in HBM, kernel timers on for the roofline leg
+    _lib.TIMERS = _lib.KernelTimers()
+    ms_total, launches, clocks = timed(step_resident, args.steps, args.warmup, with_clocks=True)
+    timers, _lib.TIMERS = _lib.TIMERS, None
+    torch.cuda.synchronize()
+    n_timed = args.steps
+    ext_ms = np.mean([a.elapsed_time(b) for a, b in timers.events['extract'][-n_timed:]])
+    int_ms = np.mean([a.elapsed_time(b) for a, b in timers.events['integrate'][-n_timed:]])
+    # --- e2e: host frames, H2D + D2H inside the timed region
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+
+    fps = world * args.steps / (ms_total / 1e3)
+    fps_e2e = world * args.steps / (ms_e2e / 1e3)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    n_rays = H * W
+    nv = float(np.mean([int((hb['mask'] & (hb['tof_depth'] != 0)).sum()) for hb in host_frames]))
+    peak, peak_src = peaks()
+    int_bytes, ext_bytes = 817.0 * nv, 364.0 * n_rays
+    roof_int = {'kernel': 'ojdf_integrate (scatter_frame_kernel + finalize_kernel)', 'bound': 'hbm',
+                'achieved': int_bytes / (int_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                'frac': int_bytes / (int_ms * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': int_bytes, 'ms_per_launch': float(int_ms)}
+    roof_ext = {'kernel': 'ojdf_extract (ray_setup_kernel + gather_kernel)', 'bound': 'hbm',
+                'achieved': ext_bytes / (ext_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                'frac': ext_bytes / (ext_ms * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': ext_bytes, 'ms_per_launch': float(ext_ms)}
+    line = {
+        'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64 ray geometry / f32 accumulation / f16+u8 volumes; networks f32 (library convs, TF32 off)',
+        'data': 'synthetic (analytic SDF room, seeded; random-init networks seed 1911)',
+        'config': {'workload': WORKLOAD, 'frame': [H, W], 'grid': GRID, 'scenes_per_gpu': SCENES_PER_RANK,
+                   'sharding': 'scenes one-per-rank, no collective',
+                   'l2': 'inputs larger than L2: %d scenes x 117 MB of volumes rotated every frame + >1 GB of network activations per frame' % SCENES_PER_RANK},
+        'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes(host_frames[0]), 'd2h_bytes_per_step': 4},
+        'gpu_launches': int(launches), 'clocks': clocks,
+        'roofline': roof_int, 'roofline_extract': roof_ext,
+        'stage_ms': {'extract': float(ext_ms), 'integrate': float(int_ms)},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_port_fps(steps=3, warmup=1)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_fps(steps, warmup, verbose=False):
+    """The reference's CPU path restated: oracle C (extract / integrate, all host threads it can use)
+    + the same torch modules on CPU for AdapNet++ and FusionNet_v3.  One step = one frame."""
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oracle.set_threads(cores)
+    dev = torch.device('cpu')
+    n_scenes = 1
+    cfg, pipe, db, frames = build_world(dev, 0, scenes_per_rank=n_scenes, frames=max(2, min(4, steps + warmup)),
+                                        render_device='cuda' if torch.cuda.is_available() else 'cpu')
+    P, T = 9, 7
+    vol = {k: None for k in db.scenes}
+    for s in db.scenes:
+        vol[s] = [db.scenes_est[s].volume.numpy().view(np.uint16), db.fusion_weights[s].numpy().view(np.uint16),
+                  db.ids_est[s].volume.numpy(), db.scores[s].volume.numpy().view(np.uint16)]
+
+    def frame(i):
+        b = frames[i % len(frames)]
+        pipe.device = dev
+        pipe._shape = b['image'].shape
+        scene = b['frame_id'][0].split('/')[0]
+        tsdf, wvol, ids, sc = vol[scene]
+        with torch.no_grad():
+            scores, sem = pipe._semantic_frame(b, as_uint8=False)
+            depth = b['tof_depth']
+            filt = torch.where(b['mask'], depth, torch.zeros_like(depth))
+            E = b['extrinsics'][0].numpy()
+            Kinv = b['intrinsics'][0].float().inverse().numpy()
+            world = oracle.unproject(depth[0].numpy(), Kinv, E)
+            res = db.resolution[scene]
+            o = oracle.extract(world, E[:3, 3], db.origin[scene].numpy(), res, tsdf, wvol)
+            values = {'fusion_values': torch.from_numpy(o['fusion_values'])[None], 'fusion_weights': torch.from_numpy(o['fusion_weights'])[None]}
+            est = pipe._fusion(pipe._prepare_fusion_input(depth, values, sem), values)
+            oracle.integrate_frame(world, filt.reshape(-1).numpy(), est[0].contiguous().numpy(), E[:3, 3], db.origin[scene].numpy(), res,
+                                   tsdf, wvol, tail=T, clampv=0.1, pix_ids=sem.reshape(-1).to(torch.uint8).numpy(),
+                                   pix_scores=scores.reshape(-1).numpy(), ids_vol=ids, scores_vol=sc, do_sem=True)
+
+    for i in range(warmup):
+        frame(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        frame(warmup + i)
+    dt = time.perf_counter() - t0
+    return {'value': steps / dt, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d frames (after %d warm-up) of the same workload on one scene: oracle C extract+integrate '
+                      '(pthreads) + torch-CPU AdapNet++/FusionNet_v3, %d threads' % (steps, warmup, cores),
+            's_per_frame': dt / steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = min(args.steps, 20)
+    warmup = min(args.warmup, 2)
+    r = cpu_port_fps(steps, warmup)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': 'frames/s', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warmup, 'ms_per_step': 1e3 * r['s_per_frame'], 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64/f32/f16 as the reference (CPU)', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'frame': [H, W], 'grid': GRID,
+                   'note': 'reference is pure Python/PyTorch and cannot travel to the GPU box; this is its CPU path restated '
+                           '(oracle C + identical torch CPU modules), pinned bit-exact to reference-generated fixtures'},
+        'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+        'e2e': {'value': r['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=60)
+    ap.add_argument('--warmup', type=int, default=6)
+    ap.add_argument('--impl', default='own', choices=['own', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == '__main__':
+    main()

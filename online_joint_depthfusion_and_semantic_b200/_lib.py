@@ -77,3 +77,52 @@ def require_cuda(*tensors):
 
 def launch_count():
     return int(lib().ojdf_launch_count())
+
+
+class KernelTimers:
+    """Optional CUDA-event brackets around the libojdf calls (bench.py's roofline leg).
+    Disabled (None) by default: no events are created on the normal path."""
+
+    def __init__(self):
+        self.events = {}
+
+    def bracket(self, name, device):
+        return _Bracket(self, name, device)
+
+    def mean_ms(self, name):
+        ev = self.events.get(name, [])
+        return sum(a.elapsed_time(b) for a, b in ev) / len(ev) if ev else None
+
+    def count(self, name):
+        return len(self.events.get(name, []))
+
+
+class _Bracket:
+    def __init__(self, timers, name, device):
+        self.t, self.name, self.device = timers, name, device
+
+    def __enter__(self):
+        self.a = torch.cuda.Event(enable_timing=True)
+        self.b = torch.cuda.Event(enable_timing=True)
+        self.a.record(torch.cuda.current_stream(self.device))
+
+    def __exit__(self, *exc):
+        self.b.record(torch.cuda.current_stream(self.device))
+        self.t.events.setdefault(self.name, []).append((self.a, self.b))
+        return False
+
+
+class _NoBracket:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+TIMERS = None
+_NO = _NoBracket()
+
+
+def timed(name, device):
+    return TIMERS.bracket(name, device) if TIMERS is not None else _NO

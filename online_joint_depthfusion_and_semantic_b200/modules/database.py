@@ -1,0 +1,100 @@
+"""Database -- the per-scene voxel state the hot path reads and writes (reference:
+modules/database.py:18-103,108-116,351-421).
+
+Volume contract (a16): per scene `scenes_est[s].volume` f16 (X,Y,Z) initialised to +init_value,
+`fusion_weights[s]` f16 zeros, `ids_est[s].volume` u8 zeros, `scores[s].volume` f16 zeros,
+`scenes_gt[s].volume` f16, `ids_gt[s].volume` u8, `origin[s]` f64 (3,) tensor, `resolution[s]` float;
+dense row-major, z fastest.  Volumes live on the GPU for their whole life (the reference's
+`efficient` implementation, modules/database.py:408-421); the mesh / HDF5 / PLY writers
+(modules/database.py:118-261) are out of scope.
+
+`dataset` only needs `.scenes` and `get_grid(scene, truncation, semantic_grid) -> (grid[, labels])`
+with `.volume`, `.origin`, `.resolution`, `.bbox` -- what modules/database.py:48-76 consumes.
+"""
+import numpy as np
+import torch
+
+
+class Voxelgrid:
+    """The four attributes of deps/graphics Voxelgrid the hot path touches (voxelgrid.py:54-70,157-161)."""
+
+    def __init__(self, resolution):
+        self.resolution = resolution
+        self.volume = None
+        self.bbox = None
+        self.origin = None
+
+    def from_array(self, array, bbox):
+        self.volume = array
+        self.bbox = np.asarray(bbox)
+        self.origin = self.bbox[:, 0].copy()
+
+    @property
+    def shape(self):
+        return tuple(self.volume.shape)
+
+
+class Database:
+
+    def __init__(self, dataset, config):
+        self.device = config.device
+        self.implementation = getattr(config, 'implementation', 'efficient')
+        self.initial_value = config.init_value
+        self.semantics = config.semantics
+        self.semantic_grid = getattr(config, 'semantic_grid', False)
+        self.scenes, self.state, self.origin, self.resolution = [], {}, {}, {}
+        self.scenes_gt, self.scenes_est, self.fusion_weights = {}, {}, {}
+        self.ids_gt, self.ids_est, self.scores = {}, {}, {}
+        for s in dataset.scenes:
+            grid = dataset.get_grid(s, self.initial_value, self.semantic_grid)
+            self.scenes.append(s)
+            self.scenes_gt[s] = grid[0]
+            self.scenes_gt[s].volume = self._dev(grid[0].volume, torch.float16)
+            self.origin[s] = torch.as_tensor(np.asarray(grid[0].origin, dtype=np.float64))
+            self.resolution[s] = float(grid[0].resolution)
+            self.scenes_est[s] = Voxelgrid(self.resolution[s])
+            self.scenes_est[s].bbox, self.scenes_est[s].origin = grid[0].bbox, grid[0].origin
+            if self.semantics:
+                if self.semantic_grid:
+                    self.ids_gt[s] = grid[1]
+                    self.ids_gt[s].volume = self._dev(grid[1].volume, torch.uint8)
+                self.ids_est[s] = Voxelgrid(self.resolution[s])
+                self.scores[s] = Voxelgrid(self.resolution[s])
+        self.reset()
+
+    def _dev(self, a, dtype):
+        t = torch.as_tensor(a) if not torch.is_tensor(a) else a
+        return t.to(device=self.device, dtype=dtype).contiguous()
+
+    def __getitem__(self, item):
+        sample = dict(origin=self.origin[item], resolution=self.resolution[item], gt=self.scenes_gt[item].volume,
+                      current=self.scenes_est[item].volume, weights=self.fusion_weights[item])
+        if self.semantics:
+            sample['ids_est'] = self.ids_est[item].volume
+            sample['scores'] = self.scores[item].volume
+            if self.semantic_grid:
+                sample['ids_gt'] = self.ids_gt[item].volume
+        else:
+            sample.update(histograms=None, ids_est=None, ids_gt=None, scores=None)
+        return sample
+
+    def __len__(self):
+        return len(self.scenes_gt)
+
+    def reset(self, scene_id=None):
+        """modules/database.py:351-371, without the numpy round trip."""
+        for s in ([scene_id] if scene_id else self.scenes):
+            shape = tuple(self.scenes_gt[s].volume.shape)
+            self.state[s] = False
+            self.scenes_est[s].volume = torch.full(shape, self.initial_value, dtype=torch.float16, device=self.device)
+            self.fusion_weights[s] = torch.zeros(shape, dtype=torch.float16, device=self.device)
+            if self.semantics:
+                self.ids_est[s].volume = torch.zeros(shape, dtype=torch.uint8, device=self.device)
+                self.scores[s].volume = torch.zeros(shape, dtype=torch.float16, device=self.device)
+
+    def filter(self, value=2.):
+        """modules/database.py:108-112."""
+        for s in self.scenes:
+            low = self.fusion_weights[s] < value
+            self.scenes_est[s].volume[low] = self.initial_value
+            self.fusion_weights[s][low] = 0

@@ -85,7 +85,7 @@ class Extractor(nn.Module):
         L = _lib.lib()
 
         def run(o_vals, o_wts, points=None, indices=None, weights=None):
-            with torch.cuda.device(dev):
+            with torch.cuda.device(dev), _lib.timed('extract' if points is None else 'extract_full', dev):
                 _lib.check(L.ojdf_extract(
                     _lib.ptr(depth_f), _lib.ptr(world_in), h, w, _lib.ptr(Kinv), _lib.ptr(E), _lib.ptr(origin_h), res,
                     _lib.ptr(tsdf_c), _lib.ptr(wvol_c), X, Y, Z, P, _lib.ptr(o_vals), _lib.ptr(o_wts), _lib.ptr(pcl),

@@ -74,7 +74,7 @@ class Integrator(torch.nn.Module):
                 ids = updates['semantics'].detach().reshape(N).to(torch.uint8).contiguous()
                 sc = updates['scores'].detach().reshape(N).float().contiguous()
             ws = self._get_workspace(N * tail * 8, dev)
-            with torch.cuda.device(dev):
+            with torch.cuda.device(dev), _lib.timed('integrate', dev):
                 _lib.check(L.ojdf_integrate(
                     _lib.ptr(ray), _lib.ptr(filt), _lib.ptr(est), N, P, tail, float(updates['clamp']),
                     values_volume.data_ptr(), weights_volume.data_ptr(), X, Y, Z, _lib.ptr(ids), _lib.ptr(sc),
@@ -91,7 +91,7 @@ class Integrator(torch.nn.Module):
                 sc = updates['scores'].to(dev).detach().reshape(M1).float().contiguous()
             if M1 > 0:
                 ws = self._get_workspace(M1 * 8, dev)
-                with torch.cuda.device(dev):
+                with torch.cuda.device(dev), _lib.timed('integrate_updates', dev):
                     _lib.check(L.ojdf_integrate_updates(
                         _lib.ptr(values), _lib.ptr(indices), _lib.ptr(weights), M1,
                         values_volume.data_ptr(), weights_volume.data_ptr(), X, Y, Z, _lib.ptr(ids), _lib.ptr(sc),

@@ -1,0 +1,174 @@
+"""Pipeline -- drop-in for the reference's modules/pipeline.py:12-363.
+
+Same construction (`Pipeline(config)`, sub-modules `_fusion_network`, `_semantic_2d_network`,
+`_extractor`, `_integrator`), same driver calls (`fuse(batch, database, device) -> None`,
+`fuse_training(batch, database, device) -> {'tsdf_est','tsdf_fused','tsdf_target'}`), same
+database protocol (reads `database[scene]`, re-binds `scenes_est/fusion_weights/ids_est/scores`,
+modules/pipeline.py:199-244) -- so test_fusion.py / train_fusion.py drive it unchanged.
+
+Per frame (modules/pipeline.py:173-248):
+  [AdapNet -> softmax -> max]  ->  Extractor  ->  FusionNet  ->  volume update  ->  Integrator
+What differs from the reference is only *how* the memory-bound steps run: the extractor and the
+integrator are one libojdf call each, and the update handed to the integrator is the compact
+`FrameUpdate` (per-ray record + network output + masked depth) instead of ~100 MB of gathered
+indices / weights / values (modules/pipeline.py:150-169).
+"""
+import torch
+from torch import nn
+
+from .adapnet import AdapNet
+from .extractor import Extractor
+from .integrator import FrameUpdate, Integrator
+from .model import FusionNet_v2, FusionNet_v3
+
+_FUSION_NETS = {'v2': FusionNet_v2, 'v3': FusionNet_v3}
+
+
+class Pipeline(nn.Module):
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.n_points = config.FUSION_MODEL.n_points
+        if config.DATA.semantics:
+            self.n_classes = config.SEMANTIC_2D_MODEL.n_classes
+        config.FUSION_MODEL.resx = config.DATA.resx
+        config.FUSION_MODEL.resy = config.DATA.resy
+        name = config.FUSION_MODEL.name
+        if name not in _FUSION_NETS:
+            raise ValueError("FUSION_MODEL.name must be 'v2' or 'v3' (the reference's 'v1' cannot be "
+                             "constructed, modules/model.py:58); got %r" % (name,))
+        self._fusion_network = _FUSION_NETS[name](config.FUSION_MODEL)
+        if config.DATA.semantics and config.DATA.semantic_strategy == 'predict':
+            self._semantic_2d_network = AdapNet(config.SEMANTIC_2D_MODEL)
+        else:
+            self._semantic_2d_network = None
+        self._extractor = Extractor(config)
+        self._integrator = Integrator(config)
+
+    # ---- a3: 2-D segmentation (modules/pipeline.py:42-60) -------------------------------------
+    def _segmentation(self, data):
+        image = (data['image'] / 255.0).to(self.device).float()       # quirk: /255 after mean/std normalisation
+        key = self.config.DATA.input
+        net = self._semantic_2d_network
+        if self.config.SEMANTIC_2D_MODEL.stage == 1:
+            src = image if key == 'image' else data[key].repeat(1, 3, 1, 1).to(self.device).float()
+            logits = net(src)[0]
+        else:
+            logits = net(image, data[key].repeat(1, 3, 1, 1).to(self.device).float())[0]
+        return torch.softmax(logits, dim=1).permute(0, 2, 3, 1)
+
+    def _semantic_frame(self, batch, as_uint8):
+        """(scores f32, ids) per pixel, or (None, None): modules/pipeline.py:181-193,277-292."""
+        if not self.config.DATA.semantics:
+            return None, None
+        strategy = self.config.DATA.semantic_strategy
+        if strategy == 'predict':
+            with torch.no_grad():
+                scores, ids = self._segmentation(batch).max(dim=-1)
+        elif strategy == 'gt':
+            ids = batch['semantic_gt'].long()
+            scores = torch.ones_like(ids).float()
+        else:
+            raise ValueError('Error! Valid value for DATA.semantic_strategy are "gt" or "predict".')
+        return scores, (ids.type(torch.uint8) if as_uint8 else ids)
+
+    # ---- a9/a11: network input / output plumbing (modules/pipeline.py:62-102) -------------------
+    def _prepare_fusion_input(self, frame, values, semantics):
+        b, _, h, w = self._shape
+        P = self.n_points
+        inputs = {
+            'tsdf_values': values['fusion_values'].view(b, h, w, P),
+            'tsdf_weights': values['fusion_weights'].view(b, h, w, P),
+            'tsdf_frame': frame.unsqueeze(-1),
+        }
+        if self.config.FUSION_MODEL.use_semantics:
+            assert semantics is not None
+            inputs['semantic_frame'] = (1 + semantics.unsqueeze(-1).float()) / self.n_classes      # (0, 1]
+        return {k: v.permute(0, 3, 1, 2).contiguous() for k, v in inputs.items()}
+
+    def _fusion(self, inputs, values):
+        b, _, h, w = self._shape
+        est = self._fusion_network(inputs).permute(0, 2, 3, 1)[..., :self.n_points]
+        return est.reshape(b, h * w, self.n_points)
+
+    # ---- a12: loss tensors (modules/pipeline.py:104-135) ------------------------------------------
+    def _prepare_fusion_output(self, values, tsdf_est, filtered_frame=None, values_gt=None):
+        b, _, h, w = self._shape
+        lim = self.config.DATA.init_value
+        old = values['fusion_values']
+        wts = values['fusion_weights'].view(b, h * w, self.n_points).clamp(min=0)
+        fused = (wts * old + torch.clamp(tsdf_est, -lim, lim)) / (wts + 1)
+        if values_gt is None:
+            return fused
+        assert filtered_frame is not None
+        keep = (filtered_frame.view(b, h * w, 1) != 0.)[0, :, 0].nonzero()[:, 0]
+        target = values_gt['fusion_values'].view(b, h * w, self.n_points)
+        return {'tsdf_est': tsdf_est, 'tsdf_fused': fused[:, keep], 'tsdf_target': target[:, keep]}
+
+    # ---- a13: volume update (modules/pipeline.py:137-171), compact form ----------------------------
+    def _prepare_volume_update(self, values, tsdf_est, tsdf_frame, semantics, scores):
+        b, _, h, w = self._shape
+        upd = FrameUpdate(ray=values['ray'], filtered_depth=tsdf_frame.reshape(h * w),
+                          est=tsdf_est.detach().reshape(h * w, -1), tail=self.config.FUSION_MODEL.n_tail_points,
+                          clamp=self.config.DATA.init_value)
+        if self.config.DATA.semantics:
+            assert semantics is not None and scores is not None
+            upd['semantics'] = semantics.to(self.device).reshape(h * w)
+            upd['scores'] = scores.to(self.device).reshape(h * w)
+        return upd
+
+    def _frames(self, batch):
+        frame = batch[self.config.DATA.input].squeeze_(1).to(self.device)
+        return frame, torch.where(batch['mask'].to(self.device), frame, torch.zeros_like(frame))
+
+    # ---- a1: inference step (modules/pipeline.py:173-248) -------------------------------------------
+    def fuse(self, batch, database, device):
+        self.device = device
+        self._shape = batch['image'].shape
+        scores, sem_ids = self._semantic_frame(batch, as_uint8=False)
+        frame, filtered_frame = self._frames(batch)
+        scene_id = batch['frame_id'][0].split('/')[0]
+        volume = database[scene_id]
+        values = self._extractor.forward(frame, batch['extrinsics'], batch['intrinsics'], volume['current'],
+                                         volume['weights'], volume['origin'], volume['resolution'])
+        tsdf_est = self._fusion(self._prepare_fusion_input(frame, values, sem_ids), values)
+        sem = self.config.DATA.semantics
+        if sem:
+            sem_ids = sem_ids.type(torch.uint8)
+        updates = self._prepare_volume_update(values, tsdf_est, filtered_frame, sem_ids if sem else None, scores)
+        tsdf, weights, ids, sc = self._integrator.forward(updates, volume['current'], volume['weights'],
+                                                          volume['scores'] if sem else None,
+                                                          volume['ids_est'] if sem else None)
+        database.state[scene_id] = True
+        database.scenes_est[scene_id].volume = tsdf
+        database.fusion_weights[scene_id] = weights
+        if sem:
+            database.ids_est[scene_id].volume = ids
+            database.scores[scene_id].volume = sc
+
+    # ---- a2: training step (modules/pipeline.py:251-363) ---------------------------------------------
+    def fuse_training(self, batch, database, device):
+        self.device = device
+        self._shape = batch['image'].shape
+        scores, sem_ids = self._semantic_frame(batch, as_uint8=True)
+        frame, filtered_frame = self._frames(batch)
+        scene_id = batch['frame_id'][0].split('/')[0]
+        volume = database[scene_id]
+        pose = (batch['extrinsics'], batch['intrinsics'])
+        values = self._extractor.forward(frame, *pose, volume['current'], volume['weights'], volume['origin'],
+                                         volume['resolution'])
+        values_gt = self._extractor.forward(frame, *pose, volume['gt'], volume['weights'], volume['origin'],
+                                            volume['resolution'])
+        tsdf_est = self._fusion(self._prepare_fusion_input(frame, values, sem_ids), values)
+        output = self._prepare_fusion_output(values, tsdf_est, filtered_frame, values_gt)
+        sem = self.config.DATA.semantics
+        updates = self._prepare_volume_update(values, tsdf_est, filtered_frame, sem_ids if sem else None, scores)
+        # the semantic volumes are not updated while training (test=False, modules/pipeline.py:349-357)
+        tsdf, weights, _, _ = self._integrator.forward(updates, volume['current'], volume['weights'],
+                                                       volume['scores'] if sem else None,
+                                                       volume['ids_est'] if sem else None, test=False)
+        database.state[scene_id] = True
+        database.scenes_est[scene_id].volume = tsdf.detach()
+        database.fusion_weights[scene_id] = weights.detach()
+        return output

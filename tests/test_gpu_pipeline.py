@@ -1,0 +1,118 @@
+"""Pipeline.fuse / fuse_training on the GPU: the plumbing around the two kernels.
+
+The network output of each frame is captured and fed to the CPU oracle, so the volumes must be
+bit-exact regardless of how the (floating-point) convolutions were computed."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from online_joint_depthfusion_and_semantic_b200.config import Config, fusion_config
+from online_joint_depthfusion_and_semantic_b200.modules.database import Database, Voxelgrid
+from online_joint_depthfusion_and_semantic_b200.modules.pipeline import Pipeline
+from online_joint_depthfusion_and_semantic_b200.synthetic import SyntheticScene
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+
+
+class _Set:
+    def __init__(self, scene):
+        self.s, self.scenes = scene, [scene.name]
+
+    def get_grid(self, name, truncation, semantic_grid):
+        sdf, lab = self.s.gt_volumes(device=DEV, truncation=truncation)
+        g = Voxelgrid(self.s.resolution); g.from_array(sdf, self.s.bbox)
+        l = Voxelgrid(self.s.resolution); l.from_array(lab, self.s.bbox)
+        return (g, l)
+
+
+def _world(h, w, G, strategy, use_sem, semantics='class30'):
+    torch.manual_seed(1911)
+    scene = SyntheticScene(name='s0', grid=G, h=h, w=w, n_frames=6, seed=5)
+    cfg = fusion_config(h, w, semantics=semantics, semantic_strategy=strategy, use_semantics=use_sem, device='cuda:0')
+    pipe = Pipeline(cfg).to(DEV).eval()
+    if pipe._semantic_2d_network is not None:
+        pipe._semantic_2d_network.set_bottleneck_dropout(False)
+    db = Database(_Set(scene), Config(device=DEV, implementation='efficient', init_value=0.1, semantics=semantics,
+                                      semantic_grid=bool(semantics)))
+    return scene, cfg, pipe, db
+
+
+@pytest.mark.parametrize('strategy,use_sem', [('gt', False), ('predict', True)])
+def test_fuse_volumes_bit_exact_given_network_output(strategy, use_sem):
+    h, w, G = 48, 64, 48
+    scene, cfg, pipe, db = _world(h, w, G, strategy, use_sem)
+    captured = {}
+    inner = pipe._fusion
+
+    def tap(inputs, values):
+        est = inner(inputs, values)
+        captured['est'] = est.detach()[0].cpu().numpy().copy()
+        captured['world'] = values['pcl'][0].cpu().numpy().copy()
+        captured['vals'] = values['fusion_values'][0].cpu().numpy().copy()
+        return est
+    pipe._fusion = tap
+    seg = {}
+    if strategy == 'predict':
+        inner_seg = pipe._semantic_frame
+
+        def seg_tap(batch, as_uint8):
+            sc, ids = inner_seg(batch, as_uint8)
+            seg['scores'], seg['ids'] = sc.reshape(-1).cpu().numpy().copy(), ids.reshape(-1).to(torch.uint8).cpu().numpy().copy()
+            return sc, ids
+        pipe._semantic_frame = seg_tap
+    t_o = np.full((G, G, G), 0.1, np.float16).view(np.uint16)
+    w_o = np.zeros((G, G, G), np.uint16); i_o = np.zeros((G, G, G), np.uint8); s_o = np.zeros((G, G, G), np.uint16)
+    with torch.no_grad():
+        for i in range(3):
+            b = scene.frame(i, device=DEV)
+            depth, mask = b['tof_depth'][0].cpu().numpy(), b['mask'][0].cpu().numpy()
+            E = b['extrinsics'][0].cpu().numpy()
+            pipe.fuse(b, db, DEV)
+            torch.cuda.synchronize()
+            o = oracle.extract(captured['world'], E[:3, 3], scene.origin, scene.resolution, t_o, w_o)
+            assert np.array_equal(o['fusion_values'].view(np.uint32), captured['vals'].view(np.uint32))
+            filt = np.where(mask, depth, np.float32(0)).reshape(-1)
+            ids = seg['ids'] if strategy == 'predict' else b['semantic_gt'].reshape(-1).cpu().numpy()
+            sc = seg['scores'] if strategy == 'predict' else np.ones(h * w, np.float32)
+            oracle.integrate_frame(captured['world'], filt, captured['est'], E[:3, 3], scene.origin, scene.resolution,
+                                   t_o, w_o, pix_ids=ids, pix_scores=sc, ids_vol=i_o, scores_vol=s_o, do_sem=True)
+    assert db.state['s0'] is True
+    assert np.array_equal(db.scenes_est['s0'].volume.cpu().numpy().view(np.uint16), t_o)
+    assert np.array_equal(db.fusion_weights['s0'].cpu().numpy().view(np.uint16), w_o)
+    assert np.array_equal(db.ids_est['s0'].volume.cpu().numpy(), i_o)
+    assert np.array_equal(db.scores['s0'].volume.cpu().numpy().view(np.uint16), s_o)
+    assert int((w_o != 0).sum()) > 1000
+
+
+def test_fuse_training_outputs_and_no_semantic_update():
+    h, w, G = 48, 64, 48
+    scene, cfg, pipe, db = _world(h, w, G, 'gt', True)
+    pipe._fusion_network.train()
+    b = scene.frame(0, device=DEV)
+    out = pipe.fuse_training(b, db, DEV)
+    nv = int((b['mask'] & (b['tof_depth'] != 0)).sum())
+    assert out['tsdf_est'].shape == (1, h * w, 9)
+    assert out['tsdf_fused'].shape == (1, nv, 9) and out['tsdf_target'].shape == (1, nv, 9)
+    assert out['tsdf_fused'].requires_grad and not out['tsdf_target'].requires_grad
+    loss = (out['tsdf_fused'] - out['tsdf_target']).abs().mean()
+    loss.backward()
+    g = [p.grad for p in pipe._fusion_network.parameters() if p.grad is not None]
+    assert len(g) > 100 and all(torch.isfinite(x).all() for x in g)
+    assert bool((db.ids_est['s0'].volume == 0).all()) and bool((db.scores['s0'].volume == 0).all())   # test=False
+    assert int((db.fusion_weights['s0'] > 0).sum()) > 1000
+    assert not db.scenes_est['s0'].volume.requires_grad
+    # the target is the trilinear read of the GT volume at the same samples
+    tgt = out['tsdf_target']
+    assert float(tgt.abs().max()) <= 0.1 + 1e-6
+
+
+def test_no_semantics_config():
+    h, w, G = 48, 64, 32
+    scene, cfg, pipe, db = _world(h, w, G, 'gt', False, semantics='')
+    assert pipe._semantic_2d_network is None
+    with torch.no_grad():
+        pipe.fuse(scene.frame(0, device=DEV), db, DEV)
+    torch.cuda.synchronize()
+    assert int((db.fusion_weights['s0'] > 0).sum()) > 500
