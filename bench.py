@@ -223,11 +223,15 @@ def run_own(args):
                 sampler.__enter__()
             l0 = _lib.launch_count()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if args.ncu_range and with_clocks:
+                torch.cuda.profiler.start()          # ncu --profile-from-start off: capture only the timed steps
             a.record()
             for i in range(steps):
                 fn(warmup + i)
             b.record()
             barrier()
+            if args.ncu_range and with_clocks:
+                torch.cuda.profiler.stop()
             launches = _lib.launch_count() - l0
             if sampler:
                 sampler.__exit__()
@@ -245,7 +249,9 @@ def run_own(args):
     ext_ms = np.mean([a.elapsed_time(b) for a, b in timers.events['extract'][-n_timed:]])
     int_ms = np.mean([a.elapsed_time(b) for a, b in timers.events['integrate'][-n_timed:]])
     # --- e2e: host frames, H2D + D2H inside the timed region
-    ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    ms_e2e = float('nan')
+    if not args.skip_e2e:
+        ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
 
     fps = world * args.steps / (ms_total / 1e3)
     fps_e2e = world * args.steps / (ms_e2e / 1e3)
@@ -365,6 +371,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=6)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ncu-range', action='store_true', help='bracket the timed value-steps with cudaProfilerStart/Stop')
+    ap.add_argument('--skip-e2e', action='store_true', help='(profiling runs only) skip the e2e leg')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

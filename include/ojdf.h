@@ -64,8 +64,9 @@ int ojdf_unproject(const float *depth_dev, int h, int w, const float *Kinv_host,
  *   eye is E[:,3] (modules/extractor.py:57)
  *   out_vals_dev / out_wts_dev   (N,P) f32   = values['fusion_values' / 'fusion_weights']
  *   out_world_dev   optional (N,3) f32       = values['pcl']
- *   out_ray_dev     optional (N,6) f64       = per-ray (centre_voxel xyz, unit direction xyz);
- *                                              the compact form ojdf_integrate() consumes
+ *   out_ray_dev     REQUIRED (N,6) f64       = per-ray (centre_voxel xyz, unit direction xyz);
+ *                                              written by the ray-setup kernel, read by the gather
+ *                                              kernel, and the compact form ojdf_integrate() consumes
  *   out_points_dev  optional (N,P,3) f64     = values['points']
  *   out_idx_dev     optional (N,P,8,3) i64   = values['indices']
  *   out_w_dev       optional (N,P,8) f64     = values['weights']
@@ -82,6 +83,9 @@ size_t ojdf_integrate_workspace_bytes(int64_t max_entries);
 /* Put a fresh (or dirty, after a failed call) workspace into its idle state.  Must be
  * enqueued once before the first ojdf_integrate*() on that workspace. */
 int ojdf_integrate_workspace_init(void *workspace_dev, size_t workspace_bytes, void *stream);
+/* Introspection for tests: the first N bytes of a workspace of this size hold the hash table and
+ * control words, and are all zero whenever no ojdf_integrate*() call is in flight. */
+size_t ojdf_integrate_workspace_idle_bytes(size_t workspace_bytes);
 
 /* ---- a13/a14/a15: _prepare_volume_update + Integrator.forward, whole-frame form ------
  * (modules/pipeline.py:137-171, modules/integrator.py:29-124).  Consumes the extractor's

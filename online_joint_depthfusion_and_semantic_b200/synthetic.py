@@ -73,12 +73,14 @@ def look_at(eye, target, up=(0.0, 0.0, 1.0)):
     return E.astype(np.float32)
 
 
-def orbit_pose(i, n, radius=0.75, height=0.35, seed=0):
-    """Pose i of an n-pose orbit around the room centre, looking across the room."""
+def orbit_pose(i, n, radius=0.75, height=0.45, seed=0):
+    """Pose i of an n-pose orbit around the room centre, looking across and down into the room.
+    The eye stays above the sphere and the cuboid (>= 0.3 m from every surface), like a hand-held
+    scan; near-surface frames are exercised by the parity tests, not by the benchmark stream."""
     rng = np.random.RandomState(1911 + 7919 * seed + i)
     a = 2.0 * math.pi * i / max(n, 1) + 0.3 * seed
-    eye = (radius * math.cos(a), radius * math.sin(a), height * math.sin(3 * a) + 0.1 * rng.randn())
-    tgt = (-0.9 * math.cos(a + 0.4), -0.9 * math.sin(a + 0.4), -0.4 + 0.3 * math.cos(2 * a))
+    eye = (radius * math.cos(a), radius * math.sin(a), height + 0.2 * math.sin(3 * a) + 0.03 * rng.randn())
+    tgt = (-0.9 * math.cos(a + 0.4), -0.9 * math.sin(a + 0.4), -0.5 + 0.3 * math.cos(2 * a))
     return look_at(eye, tgt)
 
 

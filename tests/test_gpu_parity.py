@@ -125,11 +125,11 @@ def test_integrate_frame_vs_reference_golden(golden, name):
     assert np.array_equal(_bits(tsdf), g['tsdf1'])
     assert np.array_equal(ids.cpu().numpy(), g['ids1'])
     assert np.array_equal(_bits(sc), g['scores1'])
-    # the workspace's hash table is back to idle (all ones) -> reusable without re-init
+    # the workspace's hash table and control words are back to idle (all zero) -> reusable without re-init
     ws = integ._workspace
     L = _lib.lib()
-    table_bytes = min(ws.numel(), 8 << 16)
-    assert bool((ws[:table_bytes] == 255).all())
+    idle = int(L.ojdf_integrate_workspace_idle_bytes(ws.numel()))
+    assert 0 < idle < ws.numel() and bool((ws[:idle] == 0).all())
 
 
 def test_integrate_updates_form_vs_reference_golden(golden):
@@ -197,7 +197,8 @@ def _random_frame(rs, h, w, G, ext, lo, hi, hole=0.05):
 
 @pytest.mark.parametrize('h,w,G,ext,lo,hi', [
     (240, 320, 128, 3.2, 0.3, 2.5),       # benchmark frame size, oracle-sized grid
-    (60, 80, 64, 3.2, 0.051, 0.08),       # surface 5-8 cm from the eye: hundreds of entries per voxel
+    (60, 80, 64, 3.2, 0.051, 0.08),       # surface 5-8 cm from the eye: hundreds of entries per voxel (warp path)
+    (120, 160, 32, 3.2, 0.051, 0.12),     # ... >10^4 entries per voxel (block path), 100 mm voxels
     (7, 5, 16, 1.0, 0.2, 0.6),            # ragged tiny frame, mostly out of grid
 ])
 def test_extract_and_integrate_vs_oracle_seeded(h, w, G, ext, lo, hi):
