@@ -3,25 +3,27 @@
 // The reference sums, per voxel, the contributions w and w*v of every (ray,sample,corner)
 // entry that lands in it, in ascending entry order e (CPU index_add_ order),
 // in fp32.  fp32 addition is not associative and the result is stored as fp16, so bit-exact
-// parity needs exactly that order.  The kernels below therefore do a counting sort of the
-// entries by voxel followed by a per-voxel ordering by e -- no floating-point atomics, no G^3
-// scratch, no global sort:
+// parity needs exactly that order.  The kernels below do a counting sort of the entries by voxel
+// and then RANK every entry inside its voxel -- no floating-point atomics, no G^3 scratch, no
+// global sort, no serial per-voxel sort:
 //
 //   count    : one thread per (ray,sample): recompute the 8 corners from the extractor's per-ray
 //              record, find/claim the voxel's slot in an open-addressing hash (key = linear voxel
-//              index), bump its entry count, remember the slot per entry (coalesced 32 B/thread);
-//              the thread that claims a voxel appends the slot to its block's touched list.
+//              index) and take an arrival number from its counter; slot and arrival number are
+//              remembered per entry (coalesced 64 B/thread).  The thread that claims a voxel
+//              appends the slot to its block's touched list.
 //   offsets  : one thread per touched voxel: block scan of the counts + one atomic per block gives
-//              every voxel a contiguous segment; voxels with more than 32 entries are queued for
-//              the cooperative path.
-//   place    : one thread per (ray,sample) again: write {e, w, w*v} into the voxel's segment at a
-//              cursor position (arrival order).
-//   finalize : short voxels (<= 32 entries): one thread orders its segment by e in registers/local
-//              memory; long voxels: a warp (<= 2048 entries) or a whole block sorts the segment in
-//              place with an all-ascending bitonic network (works for any length, no padding).
-//              Then the fp32 sums in ascending e, the running-mean update with fp16
-//              round-to-nearest stores (integrator.py:77-88), the semantic "highest entry wins"
-//              update (integrator.py:90-124, App. A.5), and the slot goes back to idle.
+//              every voxel a contiguous segment {off, len}; voxels longer than kRankMax are queued.
+//   scatter  : one thread per (ray,sample): write e to arrival[off + arrival number].
+//   rank     : one thread per (ray,sample): for each of its entries count the entries of the same
+//              voxel with a smaller e (a dense, independent, cache-friendly loop over the voxel's
+//              arrival segment) and store the record {e, w, w*v, label} at sorted[off + rank].
+//              Entries of over-long voxels are stored unsorted instead and a whole block sorts
+//              that segment in place with an all-ascending bitonic network.
+//   finalize : one thread per touched voxel streams its sorted segment: fp32 sums in ascending e,
+//              the running-mean update with fp16 round-to-nearest stores (integrator.py:77-88),
+//              the semantic "highest entry wins" update (integrator.py:90-124, App. A.5), and the
+//              slot goes back to idle.
 //
 // The result is deterministic and bit-identical to the single-threaded reference for every list
 // length (near-camera frames put >10^4 entries into one voxel; see tests).
@@ -30,23 +32,21 @@
 namespace ojdf {
 
 constexpr int kThreads = 256;
-constexpr int kSegment = kThreads * 8;        // entries per count/place block == max voxels a block can claim
-constexpr int kShort = 32;                    // entries ordered by a single thread
-constexpr int kWarpMax = 2048;                // entries ordered by one warp; above: one block
+constexpr int kSegment = kThreads * 8;        // entries per block == max voxels a block can claim
+constexpr int kRankMax = 2048;                // longest per-voxel list ranked by counting; above: block sort
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
-constexpr int kCoopBlocks = 148 * 2;          // persistent blocks draining the long-voxel queues
+constexpr int kCoopBlocks = 148;              // persistent blocks draining the long-voxel queue
 
 struct Workspace {
-    uint2 *table;          // {key + 1 (0 = empty), count -> cursor}; all zero when idle
+    uint4 *table;          // {key + 1 (0 = empty), arrival counter, segment offset, segment length}; zero when idle
     uint32_t *eslot;       // slot of every entry (kNoSlot = out of grid / masked)
+    uint32_t *earr;        // arrival number of every entry inside its voxel
     uint32_t *list;        // touched slots, per-block segments of kSegment
-    uint32_t *seg_off;     // segment offset of touched voxel (same indexing as list)
-    uint32_t *seg_len;     // entry count of touched voxel
-    uint4 *seg;            // {e, w bits, (w*v) bits, 0} records, grouped by voxel
-    uint32_t *queue_warp;  // touched-list positions of voxels with kShort < len <= kWarpMax
-    uint32_t *queue_block; // ... with len > kWarpMax
+    uint32_t *arrival;     // e of every entry, grouped by voxel, arrival order
+    uint4 *sorted;         // {e, w bits, (w*v) bits, label} records, grouped by voxel, ascending e
+    uint32_t *queue;       // slots of voxels with more than kRankMax entries
     uint32_t *count;       // touched voxels per block
-    uint32_t *ctrl;        // [0] segment bump cursor, [1] warp queue length, [2] block queue length; zero when idle
+    uint32_t *ctrl;        // [0] segment bump cursor, [1] queue length; zero when idle
     uint32_t slots_mask;
     int log2_slots;
 };
@@ -70,23 +70,20 @@ static size_t carve(Workspace &ws, void *base, long long cap)
     size_t off = 0;
     auto take = [&](size_t bytes) { uintptr_t p = b + off; off += align256(bytes); return p; };
     ws.ctrl = (uint32_t *)take(256);
-    ws.table = (uint2 *)take(sizeof(uint2) << l);
-    const size_t idle_bytes = off;                 // [0, idle_bytes) must be zero between calls
+    ws.table = (uint4 *)take(sizeof(uint4) << l);          // [0, here) must be zero between calls
     ws.eslot = (uint32_t *)take(4 * (size_t)cap);
+    ws.earr = (uint32_t *)take(4 * (size_t)cap);
     ws.list = (uint32_t *)take(4 * (size_t)blocks * kSegment);
-    ws.seg_off = (uint32_t *)take(4 * (size_t)blocks * kSegment);
-    ws.seg_len = (uint32_t *)take(4 * (size_t)blocks * kSegment);
-    ws.seg = (uint4 *)take(16 * (size_t)cap);
-    ws.queue_warp = (uint32_t *)take(4 * ((size_t)cap / kShort + 1));
-    ws.queue_block = (uint32_t *)take(4 * ((size_t)cap / kWarpMax + 1));
+    ws.arrival = (uint32_t *)take(4 * (size_t)cap);
+    ws.sorted = (uint4 *)take(16 * (size_t)cap);
+    ws.queue = (uint32_t *)take(4 * ((size_t)cap / kRankMax + 1));
     ws.count = (uint32_t *)take(4 * (size_t)blocks);
     ws.log2_slots = l;
     ws.slots_mask = (uint32_t)((1ull << l) - 1);
-    (void)idle_bytes;
     return off;
 }
 
-static size_t idle_prefix_bytes(long long cap) { return align256(256) + align256(sizeof(uint2) << log2_slots_for(cap)); }
+static size_t idle_prefix_bytes(long long cap) { return align256(256) + align256(sizeof(uint4) << log2_slots_for(cap)); }
 
 static long long round_up_entries(long long e) { return (e + kSegment - 1) / kSegment * kSegment; }
 
@@ -115,23 +112,6 @@ static int bind_workspace(Workspace &ws, void *base, size_t bytes, long long ent
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key, int log2_slots)
 {
     return (key * 2654435761u) >> (32 - log2_slots);
-}
-
-// Find or claim the slot of voxel `key`; is_new is set for the one thread that claimed it.
-__device__ __forceinline__ uint32_t table_insert(const Workspace &ws, uint32_t key, bool &is_new)
-{
-    const uint32_t k1 = key + 1u;
-    uint32_t s = hash_slot(key, ws.log2_slots);
-    is_new = false;
-    while (true) {
-        uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&ws.table[s].x);
-        if (cur == 0u) {
-            cur = atomicCAS(&ws.table[s].x, 0u, k1);
-            if (cur == 0u) { is_new = true; return s; }
-        }
-        if (cur == k1) return s;
-        s = (s + 1) & ws.slots_mask;
-    }
 }
 
 // The 8 (voxel key, weight) pairs of one (ray,sample); key = kNoSlot marks an out-of-grid corner.
@@ -196,6 +176,20 @@ __device__ __forceinline__ bool load_sample(const Source &src, long long t, Samp
     return true;
 }
 
+__device__ __forceinline__ void store8(uint32_t *dst, const uint32_t v[8])
+{
+    uint4 *o = reinterpret_cast<uint4 *>(dst);
+    o[0] = make_uint4(v[0], v[1], v[2], v[3]);
+    o[1] = make_uint4(v[4], v[5], v[6], v[7]);
+}
+
+__device__ __forceinline__ void load8(const uint32_t *src, uint32_t v[8])
+{
+    const uint4 *i = reinterpret_cast<const uint4 *>(src);
+    const uint4 a = i[0], b = i[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 template <bool FRAME>
 __global__ void __launch_bounds__(kThreads)
 count_kernel(Source src, Workspace ws)
@@ -208,23 +202,43 @@ count_kernel(Source src, Workspace ws)
     if (t < src.items) {
         Sample s;
         float val;
-        uint32_t slots[8];
+        uint32_t slot[8], arr[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) slots[c] = kNoSlot;
+        for (int c = 0; c < 8; ++c) { slot[c] = kNoSlot; arr[c] = 0; }
         if (load_sample<FRAME>(src, t, s, val)) {
+            uint32_t cur[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {                               // 8 independent first probes in flight
+                slot[c] = hash_slot(s.key[c], ws.log2_slots);
+                cur[c] = s.key[c] != kNoSlot ? __ldcg(&ws.table[slot[c]].x) : 0u;
+            }
+            bool is_new[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                if (s.key[c] == kNoSlot) continue;
-                bool is_new;
-                const uint32_t sl = table_insert(ws, s.key[c], is_new);
-                atomicAdd(&ws.table[sl].y, 1u);
-                slots[c] = sl;
-                if (is_new) seg_list[atomicAdd(&s_count, 1u)] = sl;
+                is_new[c] = false;
+                if (s.key[c] == kNoSlot) { slot[c] = kNoSlot; continue; }
+                const uint32_t k1 = s.key[c] + 1u;
+                uint32_t sl = slot[c], cu = cur[c];
+                while (true) {                                          // linear probing; CAS only on empty slots
+                    if (cu == 0u) {
+                        cu = atomicCAS(&ws.table[sl].x, 0u, k1);
+                        if (cu == 0u) { is_new[c] = true; break; }
+                    }
+                    if (cu == k1) break;
+                    sl = (sl + 1) & ws.slots_mask;
+                    cu = __ldcg(&ws.table[sl].x);
+                }
+                slot[c] = sl;
             }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)                                 // 8 independent counter bumps in flight
+                if (slot[c] != kNoSlot) arr[c] = atomicAdd(&ws.table[slot[c]].y, 1u);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (is_new[c]) seg_list[atomicAdd(&s_count, 1u)] = slot[c];
         }
-        uint4 *o = reinterpret_cast<uint4 *>(ws.eslot + t * 8);
-        o[0] = make_uint4(slots[0], slots[1], slots[2], slots[3]);
-        o[1] = make_uint4(slots[4], slots[5], slots[6], slots[7]);
+        store8(ws.eslot + t * 8, slot);
+        store8(ws.earr + t * 8, arr);
     }
     __syncthreads();
     if (threadIdx.x == 0) ws.count[blockIdx.x] = s_count;
@@ -257,12 +271,13 @@ offsets_kernel(Workspace ws)
     __shared__ uint32_t s_base;
     const uint32_t cnt = ws.count[blockIdx.x];
     const size_t seg0 = (size_t)blockIdx.x * kSegment;
-    uint32_t len[kSegment / kThreads], slot[kSegment / kThreads], mine = 0;
+    constexpr int R = kSegment / kThreads;
+    uint32_t len[R], slot[R], mine = 0;
 #pragma unroll
-    for (int r = 0; r < kSegment / kThreads; ++r) {                    // thread owns 8 consecutive list positions
-        const uint32_t j = threadIdx.x * (kSegment / kThreads) + r;
-        len[r] = 0;
-        if (j < cnt) { slot[r] = ws.list[seg0 + j]; len[r] = ws.table[slot[r]].y; }
+    for (int r = 0; r < R; ++r) {                                       // thread owns R consecutive list positions
+        const uint32_t j = threadIdx.x * R + r;
+        len[r] = 0; slot[r] = 0;
+        if (j < cnt) { slot[r] = ws.list[seg0 + j]; len[r] = __ldcg(&ws.table[slot[r]].y); }
         mine += len[r];
     }
     uint32_t total;
@@ -272,186 +287,169 @@ offsets_kernel(Workspace ws)
     pre += s_base;
     const uint32_t lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
 #pragma unroll
-    for (int r = 0; r < kSegment / kThreads; ++r) {
-        const uint32_t j = threadIdx.x * (kSegment / kThreads) + r;
+    for (int r = 0; r < R; ++r) {
+        const uint32_t j = threadIdx.x * R + r;
         const bool valid = j < cnt;
         if (valid) {
-            ws.seg_off[seg0 + j] = pre;
-            ws.seg_len[seg0 + j] = len[r];
-            ws.table[slot[r]].y = pre;                                 // count becomes the placement cursor
+            uint2 *zw = reinterpret_cast<uint2 *>(&ws.table[slot[r]].z);
+            *zw = make_uint2(pre, len[r]);                              // segment {off, len}
             pre += len[r];
         }
-        // queue the voxels that need a cooperative sort (warp-aggregated: one atomic per warp and class)
-        const bool qb = valid && len[r] > (uint32_t)kWarpMax;
-        const bool qw = valid && len[r] > (uint32_t)kShort && !qb;
-        const uint32_t mw = __ballot_sync(0xffffffffu, qw), mb = __ballot_sync(0xffffffffu, qb);
-        if (mw) {
-            const int leader = __ffs(mw) - 1;
+        // queue the over-long voxels (warp-aggregated: one atomic per warp)
+        const bool q = valid && len[r] > (uint32_t)kRankMax;
+        const uint32_t m = __ballot_sync(0xffffffffu, q);
+        if (m) {
+            const int leader = __ffs(m) - 1;
             uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(&ws.ctrl[1], (uint32_t)__popc(mw));
+            if ((int)lane == leader) base = atomicAdd(&ws.ctrl[1], (uint32_t)__popc(m));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (qw) ws.queue_warp[base + __popc(mw & lt_mask)] = (uint32_t)(seg0 + j);
-        }
-        if (mb) {
-            const int leader = __ffs(mb) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(&ws.ctrl[2], (uint32_t)__popc(mb));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (qb) ws.queue_block[base + __popc(mb & lt_mask)] = (uint32_t)(seg0 + j);
+            if (q) ws.queue[base + __popc(m & lt_mask)] = slot[r];
         }
     }
 }
 
+// arrival[off + arrival number] = e
+__global__ void __launch_bounds__(kThreads)
+scatter_kernel(long long items, Workspace ws)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= items) return;
+    uint32_t slot[8], arr[8], off[8];
+    load8(ws.eslot + t * 8, slot);
+    load8(ws.earr + t * 8, arr);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) off[c] = slot[c] != kNoSlot ? __ldcg(&ws.table[slot[c]].z) : 0u;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        if (slot[c] != kNoSlot) ws.arrival[off[c] + arr[c]] = (uint32_t)(t * 8 + c);
+}
+
 template <bool FRAME>
 __global__ void __launch_bounds__(kThreads)
-place_kernel(Source src, Workspace ws)
+rank_kernel(Source src, Workspace ws, const uint8_t *__restrict__ sem_ids)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     Sample s;
     float val;
     if (!load_sample<FRAME>(src, t, s, val)) return;
-    const uint4 *sp = reinterpret_cast<const uint4 *>(ws.eslot + t * 8);
-    const uint4 a = sp[0], b = sp[1];
-    const uint32_t slots[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const uint32_t label = sem_ids ? (uint32_t)sem_ids[FRAME ? t / src.T : t] : 0u;   // the sample's label rides in the record
+    uint32_t slot[8], arr[8];
+    load8(ws.eslot + t * 8, slot);
+    load8(ws.earr + t * 8, arr);
+    uint2 seg[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        seg[c] = slot[c] != kNoSlot ? __ldcg(reinterpret_cast<const uint2 *>(&ws.table[slot[c]].z)) : make_uint2(0u, 0u);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        if (slots[c] == kNoSlot) continue;
-        const uint32_t pos = atomicAdd(&ws.table[slots[c]].y, 1u);
+        if (slot[c] == kNoSlot) continue;
+        const uint32_t e = (uint32_t)(t * 8 + c), off = seg[c].x, len = seg[c].y;
+        uint32_t r = arr[c];                                            // over-long voxel: keep arrival order, sorted later
+        if (len <= (uint32_t)kRankMax) {
+            const uint32_t *a = ws.arrival + off;
+            uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, q = 0;
+            for (; q + 4 <= len; q += 4) {                              // rank = number of smaller entries of this voxel
+                r0 += a[q] < e; r1 += a[q + 1] < e; r2 += a[q + 2] < e; r3 += a[q + 3] < e;
+            }
+            for (; q < len; ++q) r0 += a[q] < e;
+            r = (r0 + r1) + (r2 + r3);
+        }
         const float u = __fmul_rn(s.w[c], val);                          // integrator.py:55, separately rounded
-        ws.seg[pos] = make_uint4((uint32_t)(t * 8 + c), __float_as_uint(s.w[c]), __float_as_uint(u), 0u);
+        ws.sorted[off + r] = make_uint4(e, __float_as_uint(s.w[c]), __float_as_uint(u), label);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 struct Volumes {
     __half *tsdf; __half *wvol; uint8_t *ids; __half *scores;
-    const uint8_t *sem_ids; const float *sem_scores;   // per record: entry e reads record e / sem_div
+    const uint8_t *sem_ids; const float *sem_scores;   // per record: entry e belongs to record e / sem_div
     uint32_t sem_div; int do_sem;
 };
 
-struct Accum {
-    float W, U; uint32_t e_last, e_label; uint8_t id_old; float sc_old;
-};
-
-__device__ __forceinline__ void accum_begin(Accum &a, const Volumes &v, uint32_t key)
-{
-    a.W = 0.0f; a.U = 0.0f; a.e_last = 0; a.e_label = kNoSlot; a.id_old = 0; a.sc_old = 0.0f;
-    if (v.do_sem) { a.id_old = v.ids[key]; a.sc_old = __half2float(v.scores[key]); }
-}
-
-__device__ __forceinline__ void accum_add(Accum &a, const Volumes &v, uint32_t e, float w, float u)
-{
-    a.W = __fadd_rn(a.W, w);                                             // index_add_, ascending e
-    a.U = __fadd_rn(a.U, u);
-    a.e_last = e;
-    if (v.do_sem && v.sem_ids[e / v.sem_div] != a.id_old) a.e_label = e;
-}
-
-__device__ __forceinline__ void accum_store(const Accum &a, const Volumes &v, uint32_t key)
-{
-    const float wo = __half2float(v.wvol[key]), vo = __half2float(v.tsdf[key]);
-    const float wn = __fadd_rn(wo, a.W);
-    v.wvol[key] = __float2half_rn(wn);                                                        // integrator.py:77-78
-    v.tsdf[key] = __float2half_rn(__fdiv_rn(__fadd_rn(__fmul_rn(wo, vo), a.U), wn));         // integrator.py:82-83 (0/0 -> NaN kept)
-    if (v.do_sem) {
-        const float s_last = v.sem_scores[a.e_last / v.sem_div];                              // highest entry wins
-        v.scores[key] = __float2half_rn(s_last > a.sc_old ? s_last : a.sc_old);               // integrator.py:112-113,124
-        if (a.e_label != kNoSlot) {
-            const uint32_t r = a.e_label / v.sem_div;
-            v.ids[key] = v.sem_scores[r] > a.sc_old ? v.sem_ids[r] : a.id_old;                 // integrator.py:115-116,123
-        }
-    }
-}
-
 // All-ascending bitonic network over seg[0..len): comparators whose upper index is >= len are
-// no-ops (virtual +inf padding), so any length sorts in place.  `tid`/`nthreads`/`sync` describe the
-// cooperating group (a warp or a block).
-template <typename Sync>
-__device__ __forceinline__ void group_sort(uint4 *seg, uint32_t len, uint32_t tid, uint32_t nthreads, Sync sync)
+// no-ops (virtual +inf padding), so any length sorts in place.
+__device__ __forceinline__ void block_sort(uint4 *seg, uint32_t len)
 {
     uint32_t P = 1;
     while (P < len) P <<= 1;
     for (uint32_t k = 2; k <= P; k <<= 1) {
-        for (uint32_t i = tid; i < P; i += nthreads) {                   // mirror step: i <-> i ^ (k-1)
+        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {        // mirror step: i <-> i ^ (k-1)
             const uint32_t j = i ^ (k - 1);
             if (j > i && j < len) {
                 const uint4 a = seg[i], b = seg[j];
                 if (a.x > b.x) { seg[i] = b; seg[j] = a; }
             }
         }
-        sync();
-        for (uint32_t s = k >> 2; s >= 1; s >>= 1) {                     // half-cleaners: i <-> i ^ s
-            for (uint32_t i = tid; i < P; i += nthreads) {
+        __syncthreads();
+        for (uint32_t s = k >> 2; s >= 1; s >>= 1) {                    // half-cleaners: i <-> i ^ s
+            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
                 const uint32_t j = i ^ s;
                 if (j > i && j < len) {
                     const uint4 a = seg[i], b = seg[j];
                     if (a.x > b.x) { seg[i] = b; seg[j] = a; }
                 }
             }
-            sync();
+            __syncthreads();
         }
     }
 }
 
-__device__ __forceinline__ void finalize_sorted(const Workspace &ws, const Volumes &vol, uint32_t pos)
+// One thread: stream the sorted segment of the voxel in `slot`, update the volumes, free the slot.
+__device__ __forceinline__ void finalize_voxel(const Workspace &ws, const Volumes &v, uint32_t slot, const uint4 entry)
 {
-    const uint32_t slot = ws.list[pos], off = ws.seg_off[pos], len = ws.seg_len[pos];
-    const uint32_t key = ws.table[slot].x - 1u;
-    ws.table[slot] = make_uint2(0u, 0u);                                 // slot back to idle for the next frame
-    Accum a;
-    accum_begin(a, vol, key);
+    const uint32_t key = entry.x - 1u, off = entry.z, len = entry.w;
+    ws.table[slot] = make_uint4(0u, 0u, 0u, 0u);                        // slot back to idle for the next frame
+    uint8_t id_old = 0;
+    float sc_old = 0.0f;
+    if (v.do_sem) { id_old = v.ids[key]; sc_old = __half2float(v.scores[key]); }
+    const float wo = __half2float(v.wvol[key]), vo = __half2float(v.tsdf[key]);
+    float W = 0.0f, U = 0.0f;
+    uint32_t e_last = 0, e_label = kNoSlot;
+    const uint4 *seg = ws.sorted + off;
     for (uint32_t q = 0; q < len; ++q) {
-        const uint4 r = ws.seg[off + q];
-        accum_add(a, vol, r.x, __uint_as_float(r.y), __uint_as_float(r.z));
+        const uint4 r = seg[q];
+        W = __fadd_rn(W, __uint_as_float(r.y));                          // index_add_, ascending e (integrator.py:60,65)
+        U = __fadd_rn(U, __uint_as_float(r.z));
+        e_last = r.x;
+        if (r.w != (uint32_t)id_old) e_label = r.x;                      // only read when do_sem
     }
-    accum_store(a, vol, key);
+    const float wn = __fadd_rn(wo, W);
+    v.wvol[key] = __float2half_rn(wn);                                                        // integrator.py:77-78
+    v.tsdf[key] = __float2half_rn(__fdiv_rn(__fadd_rn(__fmul_rn(wo, vo), U), wn));           // integrator.py:82-83 (0/0 -> NaN kept)
+    if (v.do_sem) {
+        const float s_last = v.sem_scores[e_last / v.sem_div];                                // highest entry wins
+        v.scores[key] = __float2half_rn(s_last > sc_old ? s_last : sc_old);                   // integrator.py:112-113,124
+        if (e_label != kNoSlot) {                                                             // some entry's label differs
+            const uint32_t r = e_label / v.sem_div;
+            v.ids[key] = v.sem_scores[r] > sc_old ? v.sem_ids[r] : id_old;                     // integrator.py:115-116,123
+        }
+    }
 }
 
-// grid = kCoopBlocks persistent blocks that drain the two long-voxel queues (scheduled first: they
-// are the long poles) + the count/place blocks (short voxels, one thread each).
+// grid = kCoopBlocks persistent blocks that sort + finalize the over-long voxels (scheduled first:
+// they are the long poles) followed by one block per count block (one thread per touched voxel).
 __global__ void __launch_bounds__(kThreads)
 finalize_kernel(Workspace ws, Volumes vol)
 {
-    if (blockIdx.x >= (uint32_t)kCoopBlocks) {
-        const uint32_t sb = blockIdx.x - kCoopBlocks;
-        const uint32_t cnt = ws.count[sb];
-        const size_t seg0 = (size_t)sb * kSegment;
-        for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
-            const uint32_t len = ws.seg_len[seg0 + j];
-            if (len > (uint32_t)kShort) continue;                        // handled cooperatively below
-            const uint32_t slot = ws.list[seg0 + j], off = ws.seg_off[seg0 + j];
-            const uint32_t key = ws.table[slot].x - 1u;
-            ws.table[slot] = make_uint2(0u, 0u);
-            uint32_t be[kShort];
-            float bw[kShort], bu[kShort];
-            for (uint32_t q = 0; q < len; ++q) {                         // insertion sort by e while loading
-                const uint4 r = ws.seg[off + q];
-                int p = (int)q;
-                while (p > 0 && be[p - 1] > r.x) { be[p] = be[p - 1]; bw[p] = bw[p - 1]; bu[p] = bu[p - 1]; --p; }
-                be[p] = r.x; bw[p] = __uint_as_float(r.y); bu[p] = __uint_as_float(r.z);
-            }
-            Accum a;
-            accum_begin(a, vol, key);
-            for (uint32_t q = 0; q < len; ++q) accum_add(a, vol, be[q], bw[q], bu[q]);
-            accum_store(a, vol, key);
+    if (blockIdx.x < (uint32_t)kCoopBlocks) {
+        const uint32_t nq = ws.ctrl[1];
+        for (uint32_t q = blockIdx.x; q < nq; q += kCoopBlocks) {
+            const uint32_t slot = ws.queue[q];
+            const uint4 entry = ws.table[slot];
+            block_sort(ws.sorted + entry.z, entry.w);
+            if (threadIdx.x == 0) finalize_voxel(ws, vol, slot, entry);
+            __syncthreads();
         }
         return;
     }
-    const uint32_t cb = blockIdx.x;
-    // block queue first (rare, longest), then the warp queue
-    const uint32_t nblock = ws.ctrl[2], nwarp = ws.ctrl[1];
-    for (uint32_t q = cb; q < nblock; q += kCoopBlocks) {
-        const uint32_t pos = ws.queue_block[q];
-        group_sort(ws.seg + ws.seg_off[pos], ws.seg_len[pos], threadIdx.x, blockDim.x, [] { __syncthreads(); });
-        if (threadIdx.x == 0) finalize_sorted(ws, vol, pos);
-        __syncthreads();
-    }
-    const uint32_t lane = threadIdx.x & 31, warps_total = kCoopBlocks * (kThreads / 32);
-    for (uint32_t q = cb * (kThreads / 32) + (threadIdx.x >> 5); q < nwarp; q += warps_total) {
-        const uint32_t pos = ws.queue_warp[q];
-        group_sort(ws.seg + ws.seg_off[pos], ws.seg_len[pos], lane, 32u, [] { __syncwarp(); });
-        if (lane == 0) finalize_sorted(ws, vol, pos);
-        __syncwarp();
+    const uint32_t sb = blockIdx.x - kCoopBlocks;
+    const uint32_t cnt = ws.count[sb];
+    const size_t seg0 = (size_t)sb * kSegment;
+    for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+        const uint32_t slot = ws.list[seg0 + j];
+        const uint4 entry = __ldcg(&ws.table[slot]);
+        if (entry.w > (uint32_t)kRankMax) continue;                      // handled by the cooperative blocks
+        finalize_voxel(ws, vol, slot, entry);
     }
 }
 
@@ -464,10 +462,11 @@ static int run(const Source &src, const Volumes &vol, Workspace &ws, cudaStream_
     const unsigned blocks = (unsigned)((src.items + kThreads - 1) / kThreads);
     count_kernel<FRAME><<<blocks, kThreads, 0, s>>>(src, ws);
     offsets_kernel<<<blocks, kThreads, 0, s>>>(ws);
-    place_kernel<FRAME><<<blocks, kThreads, 0, s>>>(src, ws);
+    scatter_kernel<<<blocks, kThreads, 0, s>>>(src.items, ws);
+    rank_kernel<FRAME><<<blocks, kThreads, 0, s>>>(src, ws, vol.do_sem ? vol.sem_ids : nullptr);
     finalize_kernel<<<blocks + kCoopBlocks, kThreads, 0, s>>>(ws, vol);
     reset_ctrl_kernel<<<1, 32, 0, s>>>(ws);
-    return launched(5);
+    return launched(6);
 }
 
 }  // namespace ojdf
