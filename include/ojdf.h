@@ -117,6 +117,35 @@ int ojdf_integrate_updates(const float *values_dev, const int64_t *idx_dev, cons
                            uint8_t *ids_vol_dev, void *scores_vol_dev, int do_semantics,
                            void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* ---- a10: FusionNet layers (modules/model.py:4-283), pixel-major (NHWC) fp32 activations ------
+ * One "tap GEMM" covers every convolution of FusionNet_v2/v3:
+ *   out[p, coff+co] = out_mul * act(scale[co] * sum_tap sum_ci in[p + tap*dilation, ci] * W[tap,ci,co] + shift[co])
+ * taps = 1 (1x1) or 9 (3x3, zero padding = dilation); act: 0 none, 1 ReLU, 2 LeakyReLU(slope), 3 tanh.
+ * scale/shift carry the conv bias and the inference BatchNorm (Block / Pred / VortexPooling layers).
+ * in: (H*W, in_stride) floats, in_stride % 4 == 0, channels [0,cin) are read;
+ * weights: [ceil(cout/20)][taps][4*ceil(cin/4)][20] floats, zero padded (the host mirror builds it from
+ * the module's Conv2d weight); out: (H*W, out_stride) floats. */
+int ojdf_conv_nhwc(const float *in_dev, int in_stride, int cin, int H, int W, int taps, int dilation,
+                   const float *weights_dev, const float *scale_dev, const float *shift_dev, int cout,
+                   int act, float slope, float out_mul, float *out_dev, int out_stride, int out_coffset,
+                   void *stream);
+/* nn.AvgPool2d(3, stride 1, padding 1) of VortexPooling (modules/model.py:114-116), C % 4 == 0. */
+int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int W, int C, float *out_dev, int out_stride,
+                       void *stream);
+/* VortexPooling global branch (modules/model.py:107-112) folded into the bias of the `final` 1x1 conv:
+ * shift_out[co] = f_shift[co] + f_scale[co] * sum_c wf1[co,c] * (g_scale[c]*(wg[c,:].mean_pixels(in)) + g_shift[c]).
+ * partial_dev: scratch of partial_blocks*C floats. */
+int ojdf_vortex_bias(const float *in_dev, int in_stride, int npix, int C, const float *wg_dev,
+                     const float *g_scale_dev, const float *g_shift_dev, int Cg, const float *wf1_dev,
+                     const float *f_scale_dev, const float *f_shift_dev, int Cout, float *partial_dev,
+                     int partial_blocks, float *shift_out_dev, void *stream);
+/* Network input assembly (modules/pipeline.py:74-102, modules/model.py:269,274): head A gets
+ * [values(P) | weights(P) | last_a] (the depth frame), head B (optional) [values | weights | last_b]
+ * (the normalised label frame), pixel-major with `stride` floats per pixel. */
+int ojdf_pack_fusion_input(const float *vals_dev, const float *wts_dev, const float *last_a_dev,
+                           const float *last_b_dev, int npix, int P, float *out_a_dev, float *out_b_dev,
+                           int stride, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

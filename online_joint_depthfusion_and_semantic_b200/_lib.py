@@ -28,6 +28,10 @@ _SIGNATURES = {
                             _vp, _sz, _vp]),
     'ojdf_integrate_updates': (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i,
                                     _vp, _sz, _vp]),
+    'ojdf_conv_nhwc': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _i, _i, _vp]),
+    'ojdf_avgpool3_nhwc': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    'ojdf_vortex_bias': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp]),
+    'ojdf_pack_fusion_input': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -63,11 +63,11 @@ class Pred(nn.Module):
         super().__init__()
         c = out_channels
         head = [('conv', in_channels, c, 1, 1), ('bn', c), 'lrelu', 'drop']
-        if n_points is None:
-            tail = [('conv', c, c, 1, 1), ('bn', c), 'lrelu', 'drop']
-        else:
-            tail = [('conv', c, c, 1, 1), 'lrelu', ('conv', c, n_points, 1, 1), 'tanh']
-        self.pred = _sequential(head + tail)
+        # the reference always builds the BN variant first and then replaces it for the output stage
+        # (modules/model.py:30-50); doing the same keeps seeded random initialisation identical
+        self.pred = _sequential(head + [('conv', c, c, 1, 1), ('bn', c), 'lrelu', 'drop'])
+        if n_points is not None:
+            self.pred = _sequential(head + [('conv', c, c, 1, 1), 'lrelu', ('conv', c, n_points, 1, 1), 'tanh'])
 
     def forward(self, x):
         return self.pred(x)
@@ -102,6 +102,48 @@ class VortexPooling(nn.Module):
         return self.final(torch.cat(feats, dim=1))
 
 
+class _EngineMixin:
+    """Eval-mode, no-grad, CUDA forwards run on libojdf's fused kernels (fusion_engine.py); anything
+    that needs autograd (training, row a2) runs the module's torch forward.  The launch plan is
+    dropped whenever parameters can have changed (train(), load_state_dict(), .to()/.cuda())."""
+    _engine = None
+    use_engine = True
+
+    def train(self, mode=True):
+        self._engine = None
+        return super().train(mode)
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    def engine_ready(self, ref_tensor):
+        return (self.use_engine and not self.training and not torch.is_grad_enabled() and ref_tensor.is_cuda
+                and not (hasattr(self, 'block') and self.config.use_semantics))
+
+    def forward_pixel_major(self, vals, wts, frame, sem_frame=None):
+        """vals/wts (1,N,P) pixel-major, frame (1,h,w) depth, sem_frame (1,h,w) normalised labels
+        -> est (1,N,P), already multiplied by output_scale."""
+        from .fusion_engine import FusionNetEngine
+        h, w = frame.shape[-2:]
+        e = self._engine
+        if e is None or (e.h, e.w) != (h, w) or e.device != vals.device:
+            e = self._engine = FusionNetEngine(self, h, w, vals.device)
+        return e.forward(vals, wts, frame, sem_frame)
+
+    def _forward_engine_nchw(self, x):
+        """Same call surface as the reference forward (dict of NCHW tensors in, NCHW tensor out)."""
+        b, P, h, w = x['tsdf_values'].shape
+        pm = lambda t: t.permute(0, 2, 3, 1).reshape(b, h * w, -1)           # noqa: E731
+        sem = x['semantic_frame'].reshape(b, h, w) if self.config.use_semantics else None
+        est = self.forward_pixel_major(pm(x['tsdf_values']), pm(x['tsdf_weights']), x['tsdf_frame'].reshape(b, h, w), sem)
+        return est.view(b, h, w, -1).permute(0, 3, 1, 2)
+
+
 def _dense_blocks(x, blocks):
     for blk in blocks:
         x = torch.cat([x, blk(x)], dim=1)
@@ -113,7 +155,7 @@ def _pred_stack(n_channels, gf, n_points):
                                 n_points if i == gf - 1 else None) for i in range(gf)])
 
 
-class FusionNet_v2(nn.Module):
+class FusionNet_v2(_EngineMixin, nn.Module):
     """modules/model.py:164-216: one head on [values, weights, frame(, semantics)]."""
 
     def __init__(self, config):
@@ -131,6 +173,8 @@ class FusionNet_v2(nn.Module):
         self.pred = _pred_stack(self.n_channels, self.gf, self.n_points)
 
     def forward(self, x):
+        if self.engine_ready(x['tsdf_values']):
+            return self._forward_engine_nchw(x)
         parts = [x['tsdf_values'], x['tsdf_weights'], x['tsdf_frame']]
         if self.config.use_semantics:
             parts.append(x['semantic_frame'])
@@ -139,7 +183,7 @@ class FusionNet_v2(nn.Module):
         return self.pred(y) * self.scale
 
 
-class FusionNet_v3(nn.Module):
+class FusionNet_v3(_EngineMixin, nn.Module):
     """modules/model.py:219-283: TSDF head (+ semantic head) -> vortex3 -> pred."""
 
     def __init__(self, config):
@@ -163,6 +207,8 @@ class FusionNet_v3(nn.Module):
         self.pred = _pred_stack(self.n_channels, self.gf, self.n_points)
 
     def forward(self, x):
+        if self.engine_ready(x['tsdf_values']):
+            return self._forward_engine_nchw(x)
         y = self.vortex0(_dense_blocks(torch.cat([x['tsdf_values'], x['tsdf_weights'], x['tsdf_frame']], dim=1),
                                        self.block0))
         if self.config.use_semantics:

@@ -89,7 +89,13 @@ class Pipeline(nn.Module):
 
     def _fusion(self, inputs, values):
         b, _, h, w = self._shape
-        est = self._fusion_network(inputs).permute(0, 2, 3, 1)[..., :self.n_points]
+        net = self._fusion_network
+        if getattr(net, 'engine_ready', None) is not None and net.engine_ready(values['fusion_values']):
+            # pixel-major in, pixel-major out: the extractor's layout is the kernels' layout
+            sem = inputs['semantic_frame'].reshape(b, h, w) if 'semantic_frame' in inputs else None
+            return net.forward_pixel_major(values['fusion_values'], values['fusion_weights'],
+                                           inputs['tsdf_frame'].reshape(b, h, w), sem)[..., :self.n_points]
+        est = net(inputs).permute(0, 2, 3, 1)[..., :self.n_points]
         return est.reshape(b, h * w, self.n_points)
 
     # ---- a12: loss tensors (modules/pipeline.py:104-135) ------------------------------------------
