@@ -246,8 +246,11 @@ def run_own(args):
     timers, _lib.TIMERS = _lib.TIMERS, None
     torch.cuda.synchronize()
     n_timed = args.steps
-    ext_ms = np.mean([a.elapsed_time(b) for a, b in timers.events['extract'][-n_timed:]])
-    int_ms = np.mean([a.elapsed_time(b) for a, b in timers.events['integrate'][-n_timed:]])
+    def stage(name):
+        ev = timers.events.get(name, [])[-n_timed:]
+        return float(np.mean([a.elapsed_time(b) for a, b in ev])) if ev else None
+    ext_ms, int_ms = stage('extract'), stage('integrate')
+    stages = {k: stage(k) for k in ('adapnet', 'extract', 'fusionnet', 'integrate')}
     # --- e2e: host frames, H2D + D2H inside the timed region
     ms_e2e = float('nan')
     if not args.skip_e2e:
@@ -264,7 +267,7 @@ def run_own(args):
     nv = float(np.mean([int((hb['mask'] & (hb['tof_depth'] != 0)).sum()) for hb in host_frames]))
     peak, peak_src = peaks()
     int_bytes, ext_bytes = 817.0 * nv, 364.0 * n_rays
-    roof_int = {'kernel': 'ojdf_integrate (scatter_frame_kernel + finalize_kernel)', 'bound': 'hbm',
+    roof_int = {'kernel': 'ojdf_integrate (count + offsets + scatter + rank + finalize kernels)', 'bound': 'hbm',
                 'achieved': int_bytes / (int_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
                 'frac': int_bytes / (int_ms * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': int_bytes, 'ms_per_launch': float(int_ms)}
@@ -275,7 +278,7 @@ def run_own(args):
     line = {
         'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64 ray geometry / f32 accumulation / f16+u8 volumes; networks f32 (library convs, TF32 off)',
+        'dtype': 'f64 ray geometry / f32 accumulation / f16+u8 volumes; FusionNet f32 (own fused kernels); AdapNet++ f32 (library convs, TF32 off)',
         'data': 'synthetic (analytic SDF room, seeded; random-init networks seed 1911)',
         'config': {'workload': WORKLOAD, 'frame': [H, W], 'grid': GRID, 'scenes_per_gpu': SCENES_PER_RANK,
                    'sharding': 'scenes one-per-rank, no collective',
@@ -283,7 +286,7 @@ def run_own(args):
         'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes(host_frames[0]), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'clocks': clocks,
         'roofline': roof_int, 'roofline_extract': roof_ext,
-        'stage_ms': {'extract': float(ext_ms), 'integrate': float(int_ms)},
+        'stage_ms': stages,
     }
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_port_fps(steps=3, warmup=1)

@@ -16,6 +16,7 @@ indices / weights / values (modules/pipeline.py:150-169).
 import torch
 from torch import nn
 
+from .. import _lib
 from .adapnet import AdapNet
 from .extractor import Extractor
 from .integrator import FrameUpdate, Integrator
@@ -64,7 +65,7 @@ class Pipeline(nn.Module):
             return None, None
         strategy = self.config.DATA.semantic_strategy
         if strategy == 'predict':
-            with torch.no_grad():
+            with torch.no_grad(), _lib.timed('adapnet', self.device):
                 scores, ids = self._segmentation(batch).max(dim=-1)
         elif strategy == 'gt':
             ids = batch['semantic_gt'].long()
