@@ -17,6 +17,7 @@ import torch
 from torch import nn
 
 from .. import _lib
+from ..cuda_graph import GraphedCall
 from .adapnet import AdapNet
 from .extractor import Extractor
 from .integrator import FrameUpdate, Integrator
@@ -46,18 +47,43 @@ class Pipeline(nn.Module):
             self._semantic_2d_network = None
         self._extractor = Extractor(config)
         self._integrator = Integrator(config)
+        self.use_cuda_graphs = True          # replay the fixed-shape networks as CUDA graphs in inference
+        self._seg_graph = None
+
+    def train(self, mode=True):
+        self._seg_graph = None               # captured graphs hold parameter addresses / modes
+        return super().train(mode)
+
+    def _apply(self, fn, *a, **k):
+        self._seg_graph = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._seg_graph = None
+        return super().load_state_dict(*a, **k)
 
     # ---- a3: 2-D segmentation (modules/pipeline.py:42-60) -------------------------------------
-    def _segmentation(self, data):
-        image = (data['image'] / 255.0).to(self.device).float()       # quirk: /255 after mean/std normalisation
-        key = self.config.DATA.input
+    def _segmentation_eager(self, image, aux):
+        """image (b,3,h,w) raw batch image, aux (b,h,w)|(b,1,h,w) second modality or None."""
+        image = (image / 255.0).float()                                # quirk: /255 after mean/std normalisation
         net = self._semantic_2d_network
         if self.config.SEMANTIC_2D_MODEL.stage == 1:
-            src = image if key == 'image' else data[key].repeat(1, 3, 1, 1).to(self.device).float()
-            logits = net(src)[0]
+            logits = net(image if aux is None else aux.repeat(1, 3, 1, 1).float())[0]
         else:
-            logits = net(image, data[key].repeat(1, 3, 1, 1).to(self.device).float())[0]
+            logits = net(image, aux.repeat(1, 3, 1, 1).float())[0]
         return torch.softmax(logits, dim=1).permute(0, 2, 3, 1)
+
+    def _segmentation(self, data):
+        key = self.config.DATA.input
+        image = data['image'].to(self.device)
+        aux = None if key == 'image' else data[key].to(self.device)
+        graphable = (self.use_cuda_graphs and image.is_cuda and not torch.is_grad_enabled()
+                     and not self._semantic_2d_network.training)
+        if not graphable:
+            return self._segmentation_eager(image, aux)
+        if self._seg_graph is None:
+            self._seg_graph = GraphedCall(lambda *a: self._segmentation_eager(a[0], a[1] if len(a) > 1 else None))
+        return self._seg_graph(image) if aux is None else self._seg_graph(image, aux)
 
     def _semantic_frame(self, batch, as_uint8):
         """(scores f32, ids) per pixel, or (None, None): modules/pipeline.py:181-193,277-292."""
