@@ -123,12 +123,25 @@ int ojdf_integrate_updates(const float *values_dev, const int64_t *idx_dev, cons
  * taps = 1 (1x1) or 9 (3x3, zero padding = dilation); act: 0 none, 1 ReLU, 2 LeakyReLU(slope), 3 tanh.
  * scale/shift carry the conv bias and the inference BatchNorm (Block / Pred / VortexPooling layers).
  * in: (H*W, in_stride) floats, in_stride % 4 == 0, channels [0,cin) are read;
- * weights: [ceil(cout/20)][taps][4*ceil(cin/4)][20] floats, zero padded (the host mirror builds it from
+ * weights: [ceil(cout/20)][taps][8*ceil(cin/8)][20] floats, zero padded (the host mirror builds it from
  * the module's Conv2d weight); out: (H*W, out_stride) floats. */
 int ojdf_conv_nhwc(const float *in_dev, int in_stride, int cin, int H, int W, int taps, int dilation,
                    const float *weights_dev, const float *scale_dev, const float *shift_dev, int cout,
                    int act, float slope, float out_mul, float *out_dev, int out_stride, int out_coffset,
                    void *stream);
+/* Up to 8 independent convolutions of identical shape (cin, cout, taps, H, W, activation) in ONE
+ * launch -- the two FusionNet heads, the four VortexPooling branches (each with its own dilation).
+ * `problems_host` is a host array read during the call. */
+typedef struct ojdf_conv_problem {
+    const float *in_dev;
+    const float *weights_dev;
+    const float *scale_dev;
+    const float *shift_dev;
+    float *out_dev;
+    int in_stride, out_stride, out_coffset, dilation;
+} ojdf_conv_problem;
+int ojdf_conv_nhwc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
+                           int taps, int act, float slope, float out_mul, void *stream);
 /* nn.AvgPool2d(3, stride 1, padding 1) of VortexPooling (modules/model.py:114-116), C % 4 == 0. */
 int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int W, int C, float *out_dev, int out_stride,
                        void *stream);

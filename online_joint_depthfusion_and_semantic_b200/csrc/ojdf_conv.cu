@@ -11,18 +11,36 @@
 // The arithmetic stays fp32 FMA (parity within 1e-5 of the reference's fp32 convolutions); the
 // tensor-core (tcgen05, bf16 / 3xTF32) version of the same tap-GEMM is the next step.
 //
-// conv kernel: one thread owns P pixels x 20 output channels in registers; the layer's weights for
-// one 20-channel output group live in shared memory as [tap][ci][20] and are read as broadcast
-// LDS.128; inputs are read straight from global/L1 as float4 (4 channels) per pixel and tap.
+// conv kernel (v2): one block per SM-sized pixel tile (the host sizes the tiles so that the grid is a
+// whole number of waves over the 148 SMs); up to 8 independent, equally shaped convolutions (the two
+// FusionNet heads, the four VortexPooling branches) are batched along blockIdx.z so one launch fills
+// the machine.  288 threads, each owning 2 pixels x 20 output channels in registers.  The layer's
+// weights for one 20-channel output group live in shared memory as [tap][ci][20] and are read as
+// broadcast LDS.128; the input tile is staged through shared memory in 8-channel chunks by a
+// 3-stage cp.async pipeline (coalesced 16-byte copies, zero fill for the convolution padding), so
+// global memory is read once per tap with full-sector efficiency and never through the LSU twice.
+#include <numeric>
+
 #include "ojdf_internal.h"
 
 namespace ojdf {
 
 constexpr int kGroup = 20;          // output channels per thread (19 padded to 20 for FusionNet)
-constexpr int kConvThreads = 128;
+constexpr int kCT = 288;            // threads per block (9 warps)
 constexpr int kPix = 2;             // pixels per thread
+constexpr int kTileCap = kCT * kPix;                 // 576 pixels per block at most
+constexpr int kKC = 8;              // channels per pipeline chunk
+constexpr int kRow4 = kKC / 4 + 1;  // float4 per staged pixel row (+1 pad: odd stride, conflict-free LDS.128)
+constexpr int kStages = 3;
+constexpr int kMaxBatch = 8;
 
 enum Act { kNone = 0, kRelu = 1, kLeaky = 2, kTanh = 3 };
+
+struct ConvProblem {
+    const float *in; const float *weights; const float *scale; const float *shift; float *out;
+    int in_stride, out_stride, out_coff, dil;
+};
+struct ConvBatch { ConvProblem p[kMaxBatch]; };
 
 __device__ __forceinline__ float activate(float v, int act, float slope)
 {
@@ -32,90 +50,120 @@ __device__ __forceinline__ float activate(float v, int act, float slope)
     return v;
 }
 
-// weights: [groups][taps][cin4*4][kGroup] fp32, zero padded.  Dynamic smem: taps*cin4*4*kGroup floats.
-template <int TAPS>
-__global__ void __launch_bounds__(kConvThreads)
-conv_taps_kernel(const float *__restrict__ in, int in_stride, int cin, int H, int W, int dil,
-                 const float *__restrict__ weights, const float *__restrict__ scale, const float *__restrict__ shift,
-                 int cout, int act, float slope, float out_mul, float *__restrict__ out, int out_stride, int out_coff)
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid)
 {
-    extern __shared__ float4 s_w[];
-    const int cin4 = (cin + 3) >> 2;
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;                  // 0 -> the 16 bytes are zero filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// weights: [groups][taps][cin8][kGroup] fp32, zero padded (cin8 = cin rounded up to 8).
+// dynamic smem: taps*cin8*kGroup floats of weights, then kStages input stages of kTileCap*kRow4 float4.
+template <int TAPS>
+__global__ void __launch_bounds__(kCT, 1)
+conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, int act, float slope, float out_mul)
+{
+    extern __shared__ float4 smem4[];
+    const ConvProblem pr = batch.p[blockIdx.z];
+    const int cin8 = (cin + kKC - 1) / kKC * kKC, nk = cin8 / kKC, cin4 = (cin + 3) >> 2;
     const int g = blockIdx.y;
-    const int wcount4 = TAPS * cin4 * 4 * (kGroup / 4);
-    const float4 *wg = reinterpret_cast<const float4 *>(weights) + (size_t)g * wcount4;
-    for (int i = threadIdx.x; i < wcount4; i += blockDim.x) s_w[i] = __ldg(wg + i);
-    __syncthreads();
+    const int wcount4 = TAPS * cin8 * (kGroup / 4);
+    float4 *s_w = smem4;
+    float4 *s_x = smem4 + wcount4;
+    const float4 *wg = reinterpret_cast<const float4 *>(pr.weights) + (size_t)g * wcount4;
+    for (int i = threadIdx.x; i < wcount4; i += kCT) s_w[i] = __ldg(wg + i);
 
     const int npix = H * W;
-    const int p0 = blockIdx.x * (kConvThreads * kPix) + threadIdx.x;
-    int py[kPix], px[kPix];
-    bool live[kPix];
+    const int tile0 = blockIdx.x * tile_px;
+    const int tile_end = min(tile0 + tile_px, npix);
+    // staging role: this thread copies float4 column (tid & 1) of pixels tid/2 + 144*i, i < 4
+    const int sc4 = threadIdx.x & 1;
+    int s_yx[4];
 #pragma unroll
-    for (int j = 0; j < kPix; ++j) {
-        const int p = p0 + j * kConvThreads;
-        live[j] = p < npix;
-        py[j] = live[j] ? p / W : 0;
-        px[j] = live[j] ? p - py[j] * W : 0;
+    for (int i = 0; i < 4; ++i) {
+        const int p = tile0 + (threadIdx.x >> 1) + (kCT / 2) * i;
+        const int y = p / W;
+        s_yx[i] = p < tile_end ? ((y << 16) | (p - y * W)) : -1;
     }
+    const int nchunks = TAPS * nk;
+    auto issue = [&](int ch) {
+        if (ch < nchunks) {
+            const int tap = ch / nk, k8 = ch - tap * nk;
+            const int dy = TAPS == 1 ? 0 : (tap / 3 - 1) * pr.dil, dx = TAPS == 1 ? 0 : (tap % 3 - 1) * pr.dil;
+            const int c4 = k8 * (kKC / 4) + sc4;
+            float4 *dst = s_x + (size_t)(ch % kStages) * (kTileCap * kRow4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int pl = (threadIdx.x >> 1) + (kCT / 2) * i;
+                const int y = (s_yx[i] >> 16) + dy, x = (s_yx[i] & 0xFFFF) + dx;
+                const bool ok = s_yx[i] >= 0 && c4 < cin4 && y >= 0 && y < H && x >= 0 && x < W;   // zero padding
+                const float *src = pr.in + (ok ? (size_t)(y * W + x) * pr.in_stride + c4 * 4 : 0);
+                cp_async16(dst + pl * kRow4 + sc4, src, ok);
+            }
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+
     float acc[kPix][kGroup];
 #pragma unroll
     for (int j = 0; j < kPix; ++j)
 #pragma unroll
         for (int c = 0; c < kGroup; ++c) acc[j][c] = 0.0f;
+    const int tail = cin & 3;                          // real channels in the last float4 (0 = all four)
 
-    const int tail = cin & 3;                      // channels in the last float4 that really exist (0 = all four)
-#pragma unroll 1
-    for (int tap = 0; tap < TAPS; ++tap) {
-        const int dy = TAPS == 1 ? 0 : (tap / 3 - 1) * dil, dx = TAPS == 1 ? 0 : (tap % 3 - 1) * dil;
-        const float4 *src[kPix];
-        bool ok[kPix];
+    for (int ch = 0; ch < nchunks; ++ch) {
+        cp_async_wait<1>();                            // chunk ch has landed (chunk ch+1 may still fly)
+        __syncthreads();                               // ... for every thread; stage (ch+2)%3 is free again
+        issue(ch + 2);
+        const int tap = ch / nk, k8 = ch - tap * nk;
+        const float4 *xs = s_x + (size_t)(ch % kStages) * (kTileCap * kRow4);
+        const float4 *wt = s_w + (size_t)(tap * cin8 + k8 * kKC) * (kGroup / 4);
 #pragma unroll
-        for (int j = 0; j < kPix; ++j) {
-            const int y = py[j] + dy, x = px[j] + dx;
-            ok[j] = live[j] && y >= 0 && y < H && x >= 0 && x < W;         // zero padding
-            src[j] = reinterpret_cast<const float4 *>(in + (size_t)(ok[j] ? y * W + x : 0) * in_stride);
-        }
-        const float4 *wt = s_w + tap * cin4 * 4 * (kGroup / 4);
-#pragma unroll 2
-        for (int c4 = 0; c4 < cin4; ++c4) {
+        for (int h4 = 0; h4 < kKC / 4; ++h4) {
             float4 xv[kPix];
 #pragma unroll
-            for (int j = 0; j < kPix; ++j) {
-                xv[j] = ok[j] ? __ldg(src[j] + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c4 == cin4 - 1 && tail) {      // never let a neighbouring tensor's channels in
+            for (int j = 0; j < kPix; ++j) xv[j] = xs[(threadIdx.x + j * kCT) * kRow4 + h4];
+            if (tail && k8 * (kKC / 4) + h4 == cin4 - 1) {     // never let a neighbouring tensor's channels in
+#pragma unroll
+                for (int j = 0; j < kPix; ++j) {
                     if (tail < 2) xv[j].y = 0.f;
                     if (tail < 3) xv[j].z = 0.f;
                     xv[j].w = 0.f;
                 }
             }
-            const float4 *wr = wt + c4 * 4 * (kGroup / 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
 #pragma unroll
                 for (int q = 0; q < kGroup / 4; ++q) {
-                    const float4 wv = wr[k * (kGroup / 4) + q];
+                    const float4 wv = wt[(h4 * 4 + k) * (kGroup / 4) + q];
 #pragma unroll
                     for (int j = 0; j < kPix; ++j) {
-                        const float xs = k == 0 ? xv[j].x : (k == 1 ? xv[j].y : (k == 2 ? xv[j].z : xv[j].w));
-                        acc[j][4 * q + 0] = fmaf(xs, wv.x, acc[j][4 * q + 0]);
-                        acc[j][4 * q + 1] = fmaf(xs, wv.y, acc[j][4 * q + 1]);
-                        acc[j][4 * q + 2] = fmaf(xs, wv.z, acc[j][4 * q + 2]);
-                        acc[j][4 * q + 3] = fmaf(xs, wv.w, acc[j][4 * q + 3]);
+                        const float x = k == 0 ? xv[j].x : (k == 1 ? xv[j].y : (k == 2 ? xv[j].z : xv[j].w));
+                        acc[j][4 * q + 0] = fmaf(x, wv.x, acc[j][4 * q + 0]);
+                        acc[j][4 * q + 1] = fmaf(x, wv.y, acc[j][4 * q + 1]);
+                        acc[j][4 * q + 2] = fmaf(x, wv.z, acc[j][4 * q + 2]);
+                        acc[j][4 * q + 3] = fmaf(x, wv.w, acc[j][4 * q + 3]);
                     }
                 }
             }
         }
     }
+    cp_async_wait<0>();
     const int co0 = g * kGroup;
 #pragma unroll
     for (int j = 0; j < kPix; ++j) {
-        if (!live[j]) continue;
-        float *o = out + (size_t)(p0 + j * kConvThreads) * out_stride + out_coff + co0;
+        const int p = tile0 + threadIdx.x + j * kCT;
+        if (p >= tile_end) continue;
+        float *o = pr.out + (size_t)p * pr.out_stride + pr.out_coff + co0;
 #pragma unroll
         for (int c = 0; c < kGroup; ++c) {
             if (co0 + c < cout) {
-                const float v = fmaf(acc[j][c], __ldg(scale + co0 + c), __ldg(shift + co0 + c));
+                const float v = fmaf(acc[j][c], __ldg(pr.scale + co0 + c), __ldg(pr.shift + co0 + c));
                 o[c] = activate(v, act, slope) * out_mul;
             }
         }
@@ -213,33 +261,68 @@ pack_input_kernel(const float *__restrict__ vals, const float *__restrict__ wts,
 
 using namespace ojdf;
 
+static size_t conv_smem_bytes(int taps, int cin)
+{
+    const int cin8 = (cin + kKC - 1) / kKC * kKC;
+    return ((size_t)taps * cin8 * kGroup / 4 + (size_t)kStages * kTileCap * kRow4) * sizeof(float4);
+}
+
+static int launch_conv(const ConvBatch &batch, int n, int cin, int cout, int H, int W, int taps, int act, float slope,
+                       float out_mul, cudaStream_t s)
+{
+    const size_t smem = conv_smem_bytes(taps, cin);
+    if (smem > 220 * 1024) return OJDF_ERR_TOOLARGE;
+    const int npix = H * W;
+    int sms = 148;
+    // tiles sized so that tiles * groups * problems is a whole number of waves of one block per SM
+    const int groups = (cout + kGroup - 1) / kGroup;
+    int tiles = (npix + kTileCap - 1) / kTileCap;                   // fewest tiles that fit the block capacity
+    const int per_wave = sms / std::gcd(sms, groups * n);           // tile counts that keep the total a multiple of 148
+    tiles = (tiles + per_wave - 1) / per_wave * per_wave;
+    const int tile_px = (npix + tiles - 1) / tiles;
+    tiles = (npix + tile_px - 1) / tile_px;
+    dim3 grid(tiles, groups, n);
+    if (taps == 1) {
+        static bool attr1 = false;
+        if (!attr1) { cudaFuncSetAttribute(conv_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr1 = true; }
+        conv_tile_kernel<1><<<grid, kCT, smem, s>>>(batch, cin, H, W, tile_px, cout, act, slope, out_mul);
+    } else {
+        static bool attr9 = false;
+        if (!attr9) { cudaFuncSetAttribute(conv_tile_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr9 = true; }
+        conv_tile_kernel<9><<<grid, kCT, smem, s>>>(batch, cin, H, W, tile_px, cout, act, slope, out_mul);
+    }
+    return launched(1);
+}
+
+static bool problem_ok(const ojdf_conv_problem &q, int cin, int cout)
+{
+    return q.in_dev && q.weights_dev && q.scale_dev && q.shift_dev && q.out_dev && !(q.in_stride & 3) &&
+           q.in_stride >= ((cin + 3) & ~3) && q.out_stride >= q.out_coffset + cout && q.out_coffset >= 0 && q.dilation >= 1;
+}
+
+extern "C" int ojdf_conv_nhwc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H,
+                                      int W, int taps, int act, float slope, float out_mul, void *stream)
+{
+    if (!problems_host || n_problems < 1 || n_problems > kMaxBatch || cin < 1 || cout < 1 || H < 1 || W < 1 ||
+        H > 32767 || W > 32767 || (taps != 1 && taps != 9) || act < 0 || act > 3)
+        return OJDF_ERR_BADARG;
+    ConvBatch b;
+    for (int i = 0; i < kMaxBatch; ++i) {
+        const ojdf_conv_problem &q = problems_host[i < n_problems ? i : 0];
+        if (i < n_problems && !problem_ok(q, cin, cout)) return OJDF_ERR_BADARG;
+        b.p[i] = ConvProblem{q.in_dev, q.weights_dev, q.scale_dev, q.shift_dev, q.out_dev, q.in_stride, q.out_stride,
+                             q.out_coffset, q.dilation};
+    }
+    return launch_conv(b, n_problems, cin, cout, H, W, taps, act, slope, out_mul, (cudaStream_t)stream);
+}
+
 extern "C" int ojdf_conv_nhwc(const float *in_dev, int in_stride, int cin, int H, int W, int taps, int dilation,
                               const float *weights_dev, const float *scale_dev, const float *shift_dev, int cout,
                               int act, float slope, float out_mul, float *out_dev, int out_stride, int out_coffset,
                               void *stream)
 {
-    if (!in_dev || !weights_dev || !scale_dev || !shift_dev || !out_dev || cin < 1 || cout < 1 || H < 1 || W < 1 ||
-        (taps != 1 && taps != 9) || dilation < 1 || (in_stride & 3) || in_stride < ((cin + 3) & ~3) ||
-        out_stride < out_coffset + cout || act < 0 || act > 3)
-        return OJDF_ERR_BADARG;
-    const int cin4 = (cin + 3) >> 2;
-    const size_t smem = (size_t)taps * cin4 * 4 * kGroup * sizeof(float);
-    if (smem > 200 * 1024) return OJDF_ERR_TOOLARGE;
-    const int npix = H * W;
-    dim3 grid((npix + kConvThreads * kPix - 1) / (kConvThreads * kPix), (cout + kGroup - 1) / kGroup);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (taps == 1) {
-        static bool attr1 = false;
-        if (!attr1) { cudaFuncSetAttribute(conv_taps_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr1 = true; }
-        conv_taps_kernel<1><<<grid, kConvThreads, smem, s>>>(in_dev, in_stride, cin, H, W, dilation, weights_dev, scale_dev,
-                                                             shift_dev, cout, act, slope, out_mul, out_dev, out_stride, out_coffset);
-    } else {
-        static bool attr9 = false;
-        if (!attr9) { cudaFuncSetAttribute(conv_taps_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr9 = true; }
-        conv_taps_kernel<9><<<grid, kConvThreads, smem, s>>>(in_dev, in_stride, cin, H, W, dilation, weights_dev, scale_dev,
-                                                             shift_dev, cout, act, slope, out_mul, out_dev, out_stride, out_coffset);
-    }
-    return launched(1);
+    ojdf_conv_problem q = {in_dev, weights_dev, scale_dev, shift_dev, out_dev, in_stride, out_stride, out_coffset, dilation};
+    return ojdf_conv_nhwc_batched(&q, 1, cin, cout, H, W, taps, act, slope, out_mul, stream);
 }
 
 extern "C" int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int W, int C, float *out_dev, int out_stride,

@@ -14,6 +14,8 @@ test_fusion.py:63-65); this class turns them into a launch plan over pixel-major
 Only used in eval mode under torch.no_grad(); training (autograd through FusionNet, row a2) keeps
 the module's own torch forward.  The plan is rebuilt when parameters or buffers change.
 """
+import ctypes as C
+
 import torch
 from torch import nn
 
@@ -27,8 +29,15 @@ def _pad4(c):
     return (c + 3) // 4 * 4
 
 
+class ConvProblem(C.Structure):
+    """include/ojdf.h: ojdf_conv_problem."""
+    _fields_ = [('in_dev', C.c_void_p), ('weights_dev', C.c_void_p), ('scale_dev', C.c_void_p), ('shift_dev', C.c_void_p),
+                ('out_dev', C.c_void_p), ('in_stride', C.c_int), ('out_stride', C.c_int), ('out_coffset', C.c_int),
+                ('dilation', C.c_int)]
+
+
 class _Conv:
-    """One fused conv (+BN) (+activation) launch."""
+    """One fused conv (+BN) (+activation): weights re-laid out for conv_tile_kernel."""
 
     def __init__(self, conv, bn, act, device, cin_slice=None, slope=0.01):
         w = conv.weight.detach().double()                       # (cout, cin, kh, kw)
@@ -39,7 +48,7 @@ class _Conv:
         self.taps, self.cin, self.cout = kh * kw, cin, cout
         self.dil = int(conv.dilation[0])
         assert kh == 1 or int(conv.padding[0]) == self.dil
-        groups, cin_p = (cout + _GROUP - 1) // _GROUP, _pad4(cin)
+        groups, cin_p = (cout + _GROUP - 1) // _GROUP, (cin + 7) // 8 * 8
         prep = torch.zeros(groups, self.taps, cin_p, _GROUP, dtype=torch.float64)
         wt = w.permute(2, 3, 1, 0).reshape(self.taps, cin, cout)             # [tap][ci][co], tap = ky*3+kx
         for g in range(groups):
@@ -56,36 +65,33 @@ class _Conv:
         self.shift = t.float().contiguous().to(device)
         self.act, self.slope = _ACT[act], float(slope)
 
-    def run(self, L, stream, H, W, src, src_stride, dst, dst_stride, dst_off=0, out_mul=1.0, shift=None):
-        _lib.check(L.ojdf_conv_nhwc(src.data_ptr(), src_stride, self.cin, H, W, self.taps, self.dil,
-                                    self.weights.data_ptr(), self.scale.data_ptr(),
-                                    (self.shift if shift is None else shift).data_ptr(), self.cout,
-                                    self.act, self.slope, float(out_mul), dst.data_ptr(), dst_stride, dst_off, stream))
+    def problem(self, src, src_stride, dst, dst_stride, dst_off=0, shift=None):
+        return ConvProblem(src.data_ptr(), self.weights.data_ptr(), self.scale.data_ptr(),
+                           (self.shift if shift is None else shift).data_ptr(), dst.data_ptr(), src_stride, dst_stride,
+                           dst_off, self.dil)
 
 
 class _Vortex:
     def __init__(self, m, device):
         gp_conv, gp_bn = m.gave_pool[1], m.gave_pool[3]
         self.cin, self.cout = gp_conv.in_channels, gp_conv.out_channels
-        self.mid = m.branches[0][0].out_channels
-        self.branches = []
-        for br in m.branches:
-            self.branches.append([_Conv(br[0], br[1], 'relu', device), _Conv(br[3], br[4], 'relu', device),
-                                  _Conv(br[6], br[7], 'relu', device), _Conv(br[9], br[10], 'relu', device)])
+        self.branches = [[_Conv(br[0], br[1], 'relu', device), _Conv(br[3], br[4], 'relu', device),
+                          _Conv(br[6], br[7], 'relu', device), _Conv(br[9], br[10], 'relu', device)] for br in m.branches]
         fin_conv, fin_bn = m.final[0], m.final[1]
-        C = self.cout
-        self.final = _Conv(fin_conv, fin_bn, 'none', device, cin_slice=(C, 5 * C))     # the 4 branch outputs
+        C_ = self.cout
+        self.final = _Conv(fin_conv, fin_bn, 'none', device, cin_slice=(C_, 5 * C_))     # the 4 branch outputs
         # global branch: v1 = BN(conv(mean)); its share of the final conv becomes a bias
-        self.wg = gp_conv.weight.detach().reshape(C, self.cin).float().contiguous().to(device)
+        self.wg = gp_conv.weight.detach().reshape(C_, self.cin).float().contiguous().to(device)
         gb = gp_conv.bias.detach().double()
         gs = gp_bn.weight.detach().double() / torch.sqrt(gp_bn.running_var.detach().double() + gp_bn.eps)
         self.g_scale = gs.float().to(device)
         self.g_shift = ((gb - gp_bn.running_mean.detach().double()) * gs + gp_bn.bias.detach().double()).float().to(device)
-        self.wf1 = fin_conv.weight.detach()[:, :C].reshape(C, C).float().contiguous().to(device)
-        self.frame_shift = torch.empty(C, dtype=torch.float32, device=device)
+        self.wf1 = fin_conv.weight.detach()[:, :C_].reshape(C_, C_).float().contiguous().to(device)
+        self.frame_shift = torch.empty(C_, dtype=torch.float32, device=device)
 
 
 class FusionNetEngine:
+    """Launch plan built once per (network, frame size); forward() only walks it."""
     PARTIAL_BLOCKS = 296
 
     def __init__(self, net, h, w, device):
@@ -94,98 +100,129 @@ class FusionNetEngine:
         self.scale = float(net.scale)
         self.v3 = hasattr(net, 'block0')
         self.use_sem = bool(net.config.use_semantics)
-        self.nch = int(net.n_channels)
-        self.gf = int(net.gf)
+        nch, gf = int(net.n_channels), int(net.gf)
         dev, N = self.device, self.N
+        if not self.v3 and self.use_sem:
+            raise NotImplementedError('FusionNet_v2 with a semantic input channel: use the torch forward')
 
         def blocks(ml):
             return [(_Conv(b.block[0], b.block[1], 'lrelu', dev), _Conv(b.block[4], b.block[5], 'lrelu', dev)) for b in ml]
 
-        C = self.nch * (self.gf + 1)                            # 114
-        self.C, self.Cs = C, _pad4(C)
+        Cc = nch * (gf + 1)                                     # 114
+        Cs, mid_s = _pad4(Cc), _pad4(nch)
+        self.C, self.Cs = Cc, Cs
         z = lambda c: torch.zeros(N, c, dtype=torch.float32, device=dev)     # noqa: E731
         if self.v3:
-            self.heads = [(blocks(net.block0), _Vortex(net.vortex0, dev))]
+            heads = [(blocks(net.block0), _Vortex(net.vortex0, dev))]
             if self.use_sem:
-                self.heads.append((blocks(net.block2), _Vortex(net.vortex2, dev)))
-            self.tail_vortex = [_Vortex(net.vortex3, dev)]
-            self.in_bufs = [z(self.Cs) for _ in self.heads]
-            self.cat = z(_pad4(len(self.heads) * C))
-            self.cat_stride = _pad4(len(self.heads) * C)
+                heads.append((blocks(net.block2), _Vortex(net.vortex2, dev)))
+            tail = _Vortex(net.vortex3, dev)
         else:
-            if self.use_sem:
-                raise NotImplementedError('FusionNet_v2 with a semantic input channel: use the torch forward')
-            self.heads = [(blocks(net.block), _Vortex(net.vortex, dev))]
-            self.tail_vortex = [_Vortex(net.vortex_final, dev)]
-            self.in_bufs = [z(self.Cs)]
-            self.cat, self.cat_stride = z(self.Cs), self.Cs
-        self.pred = []
+            heads, tail = [(blocks(net.block), _Vortex(net.vortex, dev))], _Vortex(net.vortex_final, dev)
+        nh = len(heads)
+        self.two = nh == 2
+        self.in_bufs = [z(Cs) for _ in range(nh)]
+        cat_stride = _pad4(nh * Cc) if self.v3 else Cs
+        self.cat = z(cat_stride)
+        self.est = torch.empty(1, N, self.P, dtype=torch.float32, device=dev)
+        self._keep = [heads, tail]                              # owns every device tensor the plan points at
+        self.partial = torch.empty(self.PARTIAL_BLOCKS * 256, dtype=torch.float32, device=dev)
+        self.plan = []
+
+        def conv_step(convs_problems):
+            """convs_problems: list of (conv, problem) with identical shapes -> one batched launch."""
+            c0 = convs_problems[0][0]
+            arr = (ConvProblem * len(convs_problems))(*[p for _, p in convs_problems])
+            self.plan.append(('conv', arr, len(convs_problems), c0.cin, c0.cout, c0.taps, c0.act, c0.slope))
+
+        # dense blocks, heads in lock step
+        t19 = [z(mid_s) for _ in range(nh)]
+        self._keep.append(t19)
+        for bi in range(gf):
+            conv_step([(heads[hh][0][bi][0], heads[hh][0][bi][0].problem(self.in_bufs[hh], Cs, t19[hh], mid_s)) for hh in range(nh)])
+            conv_step([(heads[hh][0][bi][1], heads[hh][0][bi][1].problem(t19[hh], mid_s, self.in_bufs[hh], Cs, (bi + 1) * nch))
+                       for hh in range(nh)])
+
+        def vortex_steps(vs, srcs, src_stride, dsts):
+            """vs: vortex modules run in lock step; srcs[i] -> dsts[i] = (buffer, stride, channel offset)."""
+            n = len(vs)
+            cin, Cv = vs[0].cin, vs[0].cout
+            ps = _pad4(cin)
+            pools = [[z(ps) for _ in range(3)] for _ in range(n)]
+            tb = [[[z(mid_s) for _ in range(2)] for _ in range(4)] for _ in range(n)]
+            br_out = [z(4 * Cv) for _ in range(n)]
+            self._keep += [pools, tb, br_out]
+            for i, v in enumerate(vs):
+                self.plan.append(('bias', v, srcs[i], src_stride))
+                cur, cs = srcs[i], src_stride
+                for k in range(3):                              # cascaded 3x3 average pools
+                    self.plan.append(('pool', cur, cs, ps, pools[i][k], ps))
+                    cur, cs = pools[i][k], ps
+            ins = [[(srcs[i], src_stride)] + [(pools[i][k], ps) for k in range(3)] for i in range(n)]
+            conv_step([(vs[i].branches[b][0], vs[i].branches[b][0].problem(ins[i][b][0], ins[i][b][1], tb[i][b][0], mid_s))
+                       for i in range(n) for b in range(4)])
+            conv_step([(vs[i].branches[b][1], vs[i].branches[b][1].problem(tb[i][b][0], mid_s, tb[i][b][1], mid_s))
+                       for i in range(n) for b in range(4)])
+            conv_step([(vs[i].branches[b][2], vs[i].branches[b][2].problem(tb[i][b][1], mid_s, tb[i][b][0], mid_s))
+                       for i in range(n) for b in range(4)])
+            conv_step([(vs[i].branches[b][3], vs[i].branches[b][3].problem(tb[i][b][0], mid_s, br_out[i], 4 * Cv, b * Cv))
+                       for i in range(n) for b in range(4)])
+            conv_step([(vs[i].final, vs[i].final.problem(br_out[i], 4 * Cv, dsts[i][0], dsts[i][1], dsts[i][2],
+                                                         shift=vs[i].frame_shift)) for i in range(n)])
+
+        vortex_steps([hv[1] for hv in heads], self.in_bufs, Cs, [(self.cat, cat_stride, hh * Cc) for hh in range(nh)])
+        vout = z(Cs)
+        self._keep.append(vout)
+        vortex_steps([tail], [self.cat], cat_stride, [(vout, Cs, 0)])
+
+        pred = []
         for pm in net.pred:
             seq = pm.pred
             if isinstance(seq[5], nn.BatchNorm2d):
-                self.pred += [_Conv(seq[0], seq[1], 'lrelu', dev), _Conv(seq[4], seq[5], 'lrelu', dev)]
+                pred += [_Conv(seq[0], seq[1], 'lrelu', dev), _Conv(seq[4], seq[5], 'lrelu', dev)]
             else:                                              # last Pred: conv-BN-LReLU, conv-LReLU, conv-tanh
-                self.pred += [_Conv(seq[0], seq[1], 'lrelu', dev), _Conv(seq[4], None, 'lrelu', dev),
-                              _Conv(seq[6], None, 'tanh', dev)]
-        cmax = max(v.cin for _, v in self.heads + [(None, self.tail_vortex[0])])
-        self.mid_s = _pad4(self.nch)
-        self.t19 = [z(self.mid_s) for _ in range(3)]
-        self.pool = [z(_pad4(cmax)) for _ in range(3)]
-        self.pool_stride = _pad4(cmax)
-        self.branch = z(4 * C)
-        self.vout = z(self.Cs)
-        self.pp = [z(_pad4(C)) for _ in range(2)]
-        self.partial = torch.empty(self.PARTIAL_BLOCKS * 256, dtype=torch.float32, device=dev)
-
-    def _vortex(self, L, st, v, src, src_stride, dst, dst_stride, dst_off):
-        H, W, C = self.h, self.w, v.cout
-        _lib.check(L.ojdf_vortex_bias(src.data_ptr(), src_stride, self.N, v.cin, v.wg.data_ptr(), v.g_scale.data_ptr(),
-                                      v.g_shift.data_ptr(), C, v.wf1.data_ptr(), v.final.scale.data_ptr(),
-                                      v.final.shift.data_ptr(), C, self.partial.data_ptr(), self.PARTIAL_BLOCKS,
-                                      v.frame_shift.data_ptr(), st))
-        cur, cur_stride = src, src_stride
-        for i, br in enumerate(v.branches):
-            if i > 0:                                           # cascaded 3x3 average pools
-                _lib.check(L.ojdf_avgpool3_nhwc(cur.data_ptr(), cur_stride, H, W, _pad4(v.cin), self.pool[i - 1].data_ptr(),
-                                                self.pool_stride, st))
-                cur, cur_stride = self.pool[i - 1], self.pool_stride
-            br[0].run(L, st, H, W, cur, cur_stride, self.t19[0], self.mid_s)
-            br[1].run(L, st, H, W, self.t19[0], self.mid_s, self.t19[1], self.mid_s)
-            br[2].run(L, st, H, W, self.t19[1], self.mid_s, self.t19[2], self.mid_s)
-            br[3].run(L, st, H, W, self.t19[2], self.mid_s, self.branch, 4 * C, i * C)
-        v.final.run(L, st, H, W, self.branch, 4 * C, dst, dst_stride, dst_off, shift=v.frame_shift)
+                pred += [_Conv(seq[0], seq[1], 'lrelu', dev), _Conv(seq[4], None, 'lrelu', dev), _Conv(seq[6], None, 'tanh', dev)]
+        pp = [z(Cs) for _ in range(2)]
+        self._keep += [pred, pp]
+        cur, cs = vout, Cs
+        for i, c in enumerate(pred):
+            last = i == len(pred) - 1
+            dst, ds = (self.est, self.P) if last else (pp[i % 2], Cs)
+            arr = (ConvProblem * 1)(c.problem(cur, cs, dst, ds, 0))
+            self.plan.append(('conv', arr, 1, c.cin, c.cout, c.taps, c.act, c.slope, self.scale if last else 1.0))
+            cur, cs = dst, ds
 
     def forward(self, vals, wts, frame, sem_frame=None):
         """vals / wts: (1,N,P) f32 pixel-major (Extractor output), frame: (1,h,w) f32 depth,
         sem_frame: (1,h,w) f32 normalised labels (1+id)/n_classes (modules/pipeline.py:96).
-        Returns est (1,N,P) f32."""
+        Returns est (1,N,P) f32 (a buffer owned by the engine, overwritten by the next call)."""
         _lib.require_cuda(vals, wts, frame, sem_frame)
         dev, N, H, W, P = self.device, self.N, self.h, self.w, self.P
         L = _lib.lib()
         vals = vals.detach().float().contiguous()
         wts = wts.detach().float().contiguous()
         frame = frame.detach().float().contiguous()
-        two = self.v3 and self.use_sem
-        if two:
+        if self.two:
             assert sem_frame is not None
             sem_frame = sem_frame.detach().float().contiguous()
-        est = torch.empty(1, N, P, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev), _lib.timed('fusionnet', dev):
             st = _lib.stream_ptr(dev)
             _lib.check(L.ojdf_pack_fusion_input(vals.data_ptr(), wts.data_ptr(), frame.data_ptr(),
-                                                sem_frame.data_ptr() if two else None, N, P, self.in_bufs[0].data_ptr(),
-                                                self.in_bufs[1].data_ptr() if two else None, self.Cs, st))
-            for hi, (blocks, vortex) in enumerate(self.heads):
-                buf = self.in_bufs[hi]
-                for bi, (c1, c2) in enumerate(blocks):
-                    c1.run(L, st, H, W, buf, self.Cs, self.t19[0], self.mid_s)
-                    c2.run(L, st, H, W, self.t19[0], self.mid_s, buf, self.Cs, (bi + 1) * self.nch)
-                self._vortex(L, st, vortex, buf, self.Cs, self.cat, self.cat_stride, hi * self.C)
-            self._vortex(L, st, self.tail_vortex[0], self.cat, self.cat_stride, self.vout, self.Cs, 0)
-            cur, cur_stride = self.vout, self.Cs
-            for i, c in enumerate(self.pred):
-                last = i == len(self.pred) - 1
-                dst, dst_stride = (est, P) if last else (self.pp[i % 2], self.pp[i % 2].shape[1])
-                c.run(L, st, H, W, cur, cur_stride, dst, dst_stride, 0, out_mul=self.scale if last else 1.0)
-                cur, cur_stride = dst, dst_stride
-        return est
+                                                sem_frame.data_ptr() if self.two else None, N, P, self.in_bufs[0].data_ptr(),
+                                                self.in_bufs[1].data_ptr() if self.two else None, self.Cs, st))
+            for step in self.plan:
+                kind = step[0]
+                if kind == 'conv':
+                    _, arr, n, cin, cout, taps, act, slope = step[:8]
+                    out_mul = step[8] if len(step) > 8 else 1.0
+                    _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, st))
+                elif kind == 'pool':
+                    _, src, ss, ch, dst, ds = step
+                    _lib.check(L.ojdf_avgpool3_nhwc(src.data_ptr(), ss, H, W, ch, dst.data_ptr(), ds, st))
+                else:
+                    _, v, src, ss = step
+                    _lib.check(L.ojdf_vortex_bias(src.data_ptr(), ss, N, v.cin, v.wg.data_ptr(), v.g_scale.data_ptr(),
+                                                  v.g_shift.data_ptr(), v.cout, v.wf1.data_ptr(), v.final.scale.data_ptr(),
+                                                  v.final.shift.data_ptr(), v.cout, self.partial.data_ptr(),
+                                                  self.PARTIAL_BLOCKS, v.frame_shift.data_ptr(), st))
+        return self.est
