@@ -11,14 +11,14 @@
 // The arithmetic stays fp32 FMA (parity within 1e-5 of the reference's fp32 convolutions); the
 // tensor-core (tcgen05, bf16 / 3xTF32) version of the same tap-GEMM is the next step.
 //
-// conv kernel (v2): one block per SM-sized pixel tile (the host sizes the tiles so that the grid is a
-// whole number of waves over the 148 SMs); up to 8 independent, equally shaped convolutions (the two
-// FusionNet heads, the four VortexPooling branches) are batched along blockIdx.z so one launch fills
-// the machine.  288 threads, each owning 2 pixels x 20 output channels in registers.  The layer's
-// weights for one 20-channel output group live in shared memory as [tap][ci][20] and are read as
-// broadcast LDS.128; the input tile is staged through shared memory in 8-channel chunks by a
-// 3-stage cp.async pipeline (coalesced 16-byte copies, zero fill for the convolution padding), so
-// global memory is read once per tap with full-sector efficiency and never through the LSU twice.
+// conv kernel (v3): one thread owns 4 pixels x 20 output channels in registers (80 FMAs per 6 LDS.128).
+// A block covers a pixel tile of one convolution; up to 8 independent, equally shaped convolutions
+// (the two FusionNet heads, the four VortexPooling branches) are batched along blockIdx.z and the
+// host sizes tiles / block width (96..160 threads) so that the grid is a whole number of waves over
+// the 148 SMs with several blocks co-resident per SM.  Inputs AND weights are streamed through
+// shared memory in 8-channel chunks by a 3-stage cp.async pipeline (coalesced 16-byte copies, zero
+// fill for the convolution padding): global memory is read once per tap with full-sector efficiency,
+// weights arrive as [8 ci][20 co] slices read back as broadcast LDS.128.
 #include <numeric>
 
 #include "ojdf_internal.h"
@@ -26,11 +26,11 @@
 namespace ojdf {
 
 constexpr int kGroup = 20;          // output channels per thread (19 padded to 20 for FusionNet)
-constexpr int kCT = 288;            // threads per block (9 warps)
-constexpr int kPix = 2;             // pixels per thread
-constexpr int kTileCap = kCT * kPix;                 // 576 pixels per block at most
+constexpr int kPix = 4;             // pixels per thread
+constexpr int kMaxCT = 160;         // widest block (5 warps)
 constexpr int kKC = 8;              // channels per pipeline chunk
 constexpr int kRow4 = kKC / 4 + 1;  // float4 per staged pixel row (+1 pad: odd stride, conflict-free LDS.128)
+constexpr int kWChunk4 = kKC * kGroup / 4;           // float4 of weights per chunk (8 ci x 20 co)
 constexpr int kStages = 3;
 constexpr int kMaxBatch = 8;
 
@@ -61,30 +61,28 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // weights: [groups][taps][cin8][kGroup] fp32, zero padded (cin8 = cin rounded up to 8).
-// dynamic smem: taps*cin8*kGroup floats of weights, then kStages input stages of kTileCap*kRow4 float4.
+// dynamic smem: kStages x { blockDim*kPix pixel rows of kRow4 float4, then kWChunk4 float4 of weights }.
 template <int TAPS>
-__global__ void __launch_bounds__(kCT, 1)
+__global__ void __launch_bounds__(kMaxCT)
 conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, int act, float slope, float out_mul)
 {
     extern __shared__ float4 smem4[];
     const ConvProblem pr = batch.p[blockIdx.z];
+    const int nt = blockDim.x, cap = nt * kPix;
     const int cin8 = (cin + kKC - 1) / kKC * kKC, nk = cin8 / kKC, cin4 = (cin + 3) >> 2;
     const int g = blockIdx.y;
-    const int wcount4 = TAPS * cin8 * (kGroup / 4);
-    float4 *s_w = smem4;
-    float4 *s_x = smem4 + wcount4;
-    const float4 *wg = reinterpret_cast<const float4 *>(pr.weights) + (size_t)g * wcount4;
-    for (int i = threadIdx.x; i < wcount4; i += kCT) s_w[i] = __ldg(wg + i);
+    const int stage4 = cap * kRow4 + kWChunk4;
+    const float4 *wg = reinterpret_cast<const float4 *>(pr.weights) + (size_t)g * (TAPS * cin8 * (kGroup / 4));
 
     const int npix = H * W;
     const int tile0 = blockIdx.x * tile_px;
     const int tile_end = min(tile0 + tile_px, npix);
-    // staging role: this thread copies float4 column (tid & 1) of pixels tid/2 + 144*i, i < 4
+    // staging role: this thread copies float4 column (tid & 1) of pixels tid/2 + (nt/2)*i, i < 2*kPix
     const int sc4 = threadIdx.x & 1;
-    int s_yx[4];
+    int s_yx[2 * kPix];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int p = tile0 + (threadIdx.x >> 1) + (kCT / 2) * i;
+    for (int i = 0; i < 2 * kPix; ++i) {
+        const int p = tile0 + (threadIdx.x >> 1) + (nt >> 1) * i;
         const int y = p / W;
         s_yx[i] = p < tile_end ? ((y << 16) | (p - y * W)) : -1;
     }
@@ -94,15 +92,17 @@ conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, 
             const int tap = ch / nk, k8 = ch - tap * nk;
             const int dy = TAPS == 1 ? 0 : (tap / 3 - 1) * pr.dil, dx = TAPS == 1 ? 0 : (tap % 3 - 1) * pr.dil;
             const int c4 = k8 * (kKC / 4) + sc4;
-            float4 *dst = s_x + (size_t)(ch % kStages) * (kTileCap * kRow4);
+            float4 *dst = smem4 + (size_t)(ch % kStages) * stage4;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int pl = (threadIdx.x >> 1) + (kCT / 2) * i;
+            for (int i = 0; i < 2 * kPix; ++i) {
+                const int pl = (threadIdx.x >> 1) + (nt >> 1) * i;
                 const int y = (s_yx[i] >> 16) + dy, x = (s_yx[i] & 0xFFFF) + dx;
                 const bool ok = s_yx[i] >= 0 && c4 < cin4 && y >= 0 && y < H && x >= 0 && x < W;   // zero padding
                 const float *src = pr.in + (ok ? (size_t)(y * W + x) * pr.in_stride + c4 * 4 : 0);
                 cp_async16(dst + pl * kRow4 + sc4, src, ok);
             }
+            if (threadIdx.x < kWChunk4)
+                cp_async16(dst + cap * kRow4 + threadIdx.x, wg + (size_t)(tap * cin8 + k8 * kKC) * (kGroup / 4) + threadIdx.x, true);
         }
         cp_async_commit();
     };
@@ -120,14 +120,14 @@ conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, 
         cp_async_wait<1>();                            // chunk ch has landed (chunk ch+1 may still fly)
         __syncthreads();                               // ... for every thread; stage (ch+2)%3 is free again
         issue(ch + 2);
-        const int tap = ch / nk, k8 = ch - tap * nk;
-        const float4 *xs = s_x + (size_t)(ch % kStages) * (kTileCap * kRow4);
-        const float4 *wt = s_w + (size_t)(tap * cin8 + k8 * kKC) * (kGroup / 4);
+        const int k8 = ch % nk;
+        const float4 *xs = smem4 + (size_t)(ch % kStages) * stage4;
+        const float4 *wt = xs + cap * kRow4;
 #pragma unroll
         for (int h4 = 0; h4 < kKC / 4; ++h4) {
             float4 xv[kPix];
 #pragma unroll
-            for (int j = 0; j < kPix; ++j) xv[j] = xs[(threadIdx.x + j * kCT) * kRow4 + h4];
+            for (int j = 0; j < kPix; ++j) xv[j] = xs[(threadIdx.x + j * nt) * kRow4 + h4];
             if (tail && k8 * (kKC / 4) + h4 == cin4 - 1) {     // never let a neighbouring tensor's channels in
 #pragma unroll
                 for (int j = 0; j < kPix; ++j) {
@@ -157,7 +157,7 @@ conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, 
     const int co0 = g * kGroup;
 #pragma unroll
     for (int j = 0; j < kPix; ++j) {
-        const int p = tile0 + threadIdx.x + j * kCT;
+        const int p = tile0 + threadIdx.x + j * nt;
         if (p >= tile_end) continue;
         float *o = pr.out + (size_t)p * pr.out_stride + pr.out_coff + co0;
 #pragma unroll
@@ -261,35 +261,40 @@ pack_input_kernel(const float *__restrict__ vals, const float *__restrict__ wts,
 
 using namespace ojdf;
 
-static size_t conv_smem_bytes(int taps, int cin)
+// Pick the tile count and block width: whole waves over the SMs, lanes as full as possible.
+static void conv_geometry(int npix, int blocks_per_tile, int &tiles, int &tile_px, int &threads)
 {
-    const int cin8 = (cin + kKC - 1) / kKC * kKC;
-    return ((size_t)taps * cin8 * kGroup / 4 + (size_t)kStages * kTileCap * kRow4) * sizeof(float4);
+    const int sms = 148;
+    double best = 1e30;
+    const int tmin = (npix + kMaxCT * kPix - 1) / (kMaxCT * kPix);
+    for (int t = tmin; t <= tmin * 4 + sms; ++t) {
+        const int px = (npix + t - 1) / t;
+        const int th = ((px + kPix - 1) / kPix + 31) / 32 * 32;
+        if (th > kMaxCT) continue;
+        const int real_tiles = (npix + px - 1) / px;
+        const long long blocks = (long long)real_tiles * blocks_per_tile;
+        const double cost = (double)((blocks + sms - 1) / sms) * th;   // rounds x time per round
+        if (cost < best - 1e-9) { best = cost; tiles = real_tiles; tile_px = px; threads = th; }
+    }
 }
 
 static int launch_conv(const ConvBatch &batch, int n, int cin, int cout, int H, int W, int taps, int act, float slope,
                        float out_mul, cudaStream_t s)
 {
-    const size_t smem = conv_smem_bytes(taps, cin);
-    if (smem > 220 * 1024) return OJDF_ERR_TOOLARGE;
     const int npix = H * W;
-    int sms = 148;
-    // tiles sized so that tiles * groups * problems is a whole number of waves of one block per SM
     const int groups = (cout + kGroup - 1) / kGroup;
-    int tiles = (npix + kTileCap - 1) / kTileCap;                   // fewest tiles that fit the block capacity
-    const int per_wave = sms / std::gcd(sms, groups * n);           // tile counts that keep the total a multiple of 148
-    tiles = (tiles + per_wave - 1) / per_wave * per_wave;
-    const int tile_px = (npix + tiles - 1) / tiles;
-    tiles = (npix + tile_px - 1) / tile_px;
+    int tiles = 1, tile_px = npix, threads = 32;
+    conv_geometry(npix, groups * n, tiles, tile_px, threads);
+    const size_t smem = (size_t)kStages * ((size_t)threads * kPix * kRow4 + kWChunk4) * sizeof(float4);
     dim3 grid(tiles, groups, n);
     if (taps == 1) {
         static bool attr1 = false;
-        if (!attr1) { cudaFuncSetAttribute(conv_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr1 = true; }
-        conv_tile_kernel<1><<<grid, kCT, smem, s>>>(batch, cin, H, W, tile_px, cout, act, slope, out_mul);
+        if (!attr1) { cudaFuncSetAttribute(conv_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr1 = true; }
+        conv_tile_kernel<1><<<grid, threads, smem, s>>>(batch, cin, H, W, tile_px, cout, act, slope, out_mul);
     } else {
         static bool attr9 = false;
-        if (!attr9) { cudaFuncSetAttribute(conv_tile_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr9 = true; }
-        conv_tile_kernel<9><<<grid, kCT, smem, s>>>(batch, cin, H, W, tile_px, cout, act, slope, out_mul);
+        if (!attr9) { cudaFuncSetAttribute(conv_tile_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr9 = true; }
+        conv_tile_kernel<9><<<grid, threads, smem, s>>>(batch, cin, H, W, tile_px, cout, act, slope, out_mul);
     }
     return launched(1);
 }
