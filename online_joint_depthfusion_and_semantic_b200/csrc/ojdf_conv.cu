@@ -101,8 +101,8 @@ conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, 
                 const float *src = pr.in + (ok ? (size_t)(y * W + x) * pr.in_stride + c4 * 4 : 0);
                 cp_async16(dst + pl * kRow4 + sc4, src, ok);
             }
-            if (threadIdx.x < kWChunk4)
-                cp_async16(dst + cap * kRow4 + threadIdx.x, wg + (size_t)(tap * cin8 + k8 * kKC) * (kGroup / 4) + threadIdx.x, true);
+            for (int i = threadIdx.x; i < kWChunk4; i += nt)       // 40 float4 of weights: [8 ci][20 co]
+                cp_async16(dst + cap * kRow4 + i, wg + (size_t)(tap * cin8 + k8 * kKC) * (kGroup / 4) + i, true);
         }
         cp_async_commit();
     };
