@@ -11,7 +11,8 @@
 // The arithmetic stays fp32 FMA (parity within 1e-5 of the reference's fp32 convolutions); the
 // tensor-core (tcgen05, bf16 / 3xTF32) version of the same tap-GEMM is the next step.
 //
-// conv kernel (v3): one thread owns 4 pixels x 20 output channels in registers (80 FMAs per 6 LDS.128).
+// conv kernel (v4): one thread owns 4 pixels x 20 output channels in registers (80 FMAs per 6 LDS.128),
+// one warp owns 128 consecutive pixels and runs its own barrier-free cp.async pipeline.
 // A block covers a pixel tile of one convolution; up to 8 independent, equally shaped convolutions
 // (the two FusionNet heads, the four VortexPooling branches) are batched along blockIdx.z and the
 // host sizes tiles / block width (96..160 threads) so that the grid is a whole number of waves over
@@ -61,48 +62,66 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // weights: [groups][taps][cin8][kGroup] fp32, zero padded (cin8 = cin rounded up to 8).
-// dynamic smem: kStages x { blockDim*kPix pixel rows of kRow4 float4, then kWChunk4 float4 of weights }.
+// dynamic smem: per warp, kStages x { 128 pixel rows of kRow4 float4, then kWChunk4 float4 of weights }.
+// Every warp runs its own cp.async pipeline over its own 128 pixels (lane l owns pixels l, l+32, l+64,
+// l+96 of the warp's slice), so the main loop has no block-wide barrier at all.
+constexpr int kWarpPix = 32 * kPix;                            // 128
+constexpr int kWarpStage4 = kWarpPix * kRow4 + kWChunk4;       // float4 per warp per stage
+
 template <int TAPS>
-__global__ void __launch_bounds__(kMaxCT)
+__global__ void __launch_bounds__(kMaxCT, 3)
 conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, int act, float slope, float out_mul)
 {
     extern __shared__ float4 smem4[];
     const ConvProblem pr = batch.p[blockIdx.z];
-    const int nt = blockDim.x, cap = nt * kPix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cin8 = (cin + kKC - 1) / kKC * kKC, nk = cin8 / kKC, cin4 = (cin + 3) >> 2;
     const int g = blockIdx.y;
-    const int stage4 = cap * kRow4 + kWChunk4;
     const float4 *wg = reinterpret_cast<const float4 *>(pr.weights) + (size_t)g * (TAPS * cin8 * (kGroup / 4));
+    float4 *wsm = smem4 + (size_t)warp * (kStages * kWarpStage4);
 
     const int npix = H * W;
-    const int tile0 = blockIdx.x * tile_px;
-    const int tile_end = min(tile0 + tile_px, npix);
-    // staging role: this thread copies float4 column (tid & 1) of pixels tid/2 + (nt/2)*i, i < 2*kPix
-    const int sc4 = threadIdx.x & 1;
-    int s_yx[2 * kPix];
+    const int tile0 = blockIdx.x * tile_px + warp * kWarpPix;
+    const int tile_end = min(blockIdx.x * tile_px + tile_px, npix);
+    // staging role: this lane copies float4 column (lane & 1) of the warp's pixels lane/2 + 16*i, i < 8.
+    // Per staged pixel: element offset of the pixel row and a 9-bit mask of the taps that stay inside
+    // the image (zero padding elsewhere).
+    const int sc4 = lane & 1;
+    int s_off[2 * kPix];
+    unsigned s_ok[2 * kPix];
 #pragma unroll
     for (int i = 0; i < 2 * kPix; ++i) {
-        const int p = tile0 + (threadIdx.x >> 1) + (nt >> 1) * i;
-        const int y = p / W;
-        s_yx[i] = p < tile_end ? ((y << 16) | (p - y * W)) : -1;
+        const int p = tile0 + (lane >> 1) + 16 * i;
+        const int y = p / W, x = p - y * W;
+        s_off[i] = p * pr.in_stride;
+        unsigned m = 0;
+        if (p < tile_end) {
+#pragma unroll
+            for (int tap = 0; tap < TAPS; ++tap) {
+                const int yy = y + (TAPS == 1 ? 0 : (tap / 3 - 1) * pr.dil), xx = x + (TAPS == 1 ? 0 : (tap % 3 - 1) * pr.dil);
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) m |= 1u << tap;
+            }
+        }
+        s_ok[i] = m;
     }
     const int nchunks = TAPS * nk;
+    int i_tap = 0, i_k8 = 0;                               // (tap, k8) of the next chunk to issue
     auto issue = [&](int ch) {
         if (ch < nchunks) {
-            const int tap = ch / nk, k8 = ch - tap * nk;
-            const int dy = TAPS == 1 ? 0 : (tap / 3 - 1) * pr.dil, dx = TAPS == 1 ? 0 : (tap % 3 - 1) * pr.dil;
-            const int c4 = k8 * (kKC / 4) + sc4;
-            float4 *dst = smem4 + (size_t)(ch % kStages) * stage4;
+            const int dy = TAPS == 1 ? 0 : (i_tap / 3 - 1) * pr.dil, dx = TAPS == 1 ? 0 : (i_tap % 3 - 1) * pr.dil;
+            const int c4 = i_k8 * (kKC / 4) + sc4;
+            const int shift = (dy * W + dx) * pr.in_stride + c4 * 4;
+            const bool col_ok = c4 < cin4;
+            float4 *dst = wsm + (size_t)(ch % kStages) * kWarpStage4;
 #pragma unroll
             for (int i = 0; i < 2 * kPix; ++i) {
-                const int pl = (threadIdx.x >> 1) + (nt >> 1) * i;
-                const int y = (s_yx[i] >> 16) + dy, x = (s_yx[i] & 0xFFFF) + dx;
-                const bool ok = s_yx[i] >= 0 && c4 < cin4 && y >= 0 && y < H && x >= 0 && x < W;   // zero padding
-                const float *src = pr.in + (ok ? (size_t)(y * W + x) * pr.in_stride + c4 * 4 : 0);
-                cp_async16(dst + pl * kRow4 + sc4, src, ok);
+                const bool ok = col_ok && ((s_ok[i] >> i_tap) & 1u);
+                cp_async16(dst + ((lane >> 1) + 16 * i) * kRow4 + sc4, pr.in + (ok ? s_off[i] + shift : 0), ok);
             }
-            for (int i = threadIdx.x; i < kWChunk4; i += nt)       // 40 float4 of weights: [8 ci][20 co]
-                cp_async16(dst + cap * kRow4 + i, wg + (size_t)(tap * cin8 + k8 * kKC) * (kGroup / 4) + i, true);
+            const float4 *wsrc = wg + (size_t)(i_tap * cin8 + i_k8 * kKC) * (kGroup / 4);
+            cp_async16(dst + kWarpPix * kRow4 + lane, wsrc + lane, true);
+            if (lane < kWChunk4 - 32) cp_async16(dst + kWarpPix * kRow4 + 32 + lane, wsrc + 32 + lane, true);
+            if (++i_k8 == nk) { i_k8 = 0; ++i_tap; }
         }
         cp_async_commit();
     };
@@ -116,18 +135,18 @@ conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, 
         for (int c = 0; c < kGroup; ++c) acc[j][c] = 0.0f;
     const int tail = cin & 3;                          // real channels in the last float4 (0 = all four)
 
+    int k8 = 0;
     for (int ch = 0; ch < nchunks; ++ch) {
-        cp_async_wait<1>();                            // chunk ch has landed (chunk ch+1 may still fly)
-        __syncthreads();                               // ... for every thread; stage (ch+2)%3 is free again
+        cp_async_wait<1>();                            // this lane's copies of chunk ch have landed
+        __syncwarp();                                  // ... and every lane's; stage (ch+2)%3 is free again
         issue(ch + 2);
-        const int k8 = ch % nk;
-        const float4 *xs = smem4 + (size_t)(ch % kStages) * stage4;
-        const float4 *wt = xs + cap * kRow4;
+        const float4 *xs = wsm + (size_t)(ch % kStages) * kWarpStage4;
+        const float4 *wt = xs + kWarpPix * kRow4;
 #pragma unroll
         for (int h4 = 0; h4 < kKC / 4; ++h4) {
             float4 xv[kPix];
 #pragma unroll
-            for (int j = 0; j < kPix; ++j) xv[j] = xs[(threadIdx.x + j * nt) * kRow4 + h4];
+            for (int j = 0; j < kPix; ++j) xv[j] = xs[(lane + 32 * j) * kRow4 + h4];
             if (tail && k8 * (kKC / 4) + h4 == cin4 - 1) {     // never let a neighbouring tensor's channels in
 #pragma unroll
                 for (int j = 0; j < kPix; ++j) {
@@ -152,21 +171,25 @@ conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, 
                 }
             }
         }
+        if (++k8 == nk) k8 = 0;
     }
     cp_async_wait<0>();
     const int co0 = g * kGroup;
+    float sc[kGroup], sh[kGroup];
+#pragma unroll
+    for (int c = 0; c < kGroup; ++c) {
+        const bool live = co0 + c < cout;
+        sc[c] = live ? __ldg(pr.scale + co0 + c) : 0.f;
+        sh[c] = live ? __ldg(pr.shift + co0 + c) : 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < kPix; ++j) {
-        const int p = tile0 + threadIdx.x + j * nt;
+        const int p = tile0 + lane + 32 * j;
         if (p >= tile_end) continue;
         float *o = pr.out + (size_t)p * pr.out_stride + pr.out_coff + co0;
 #pragma unroll
-        for (int c = 0; c < kGroup; ++c) {
-            if (co0 + c < cout) {
-                const float v = fmaf(acc[j][c], __ldg(pr.scale + co0 + c), __ldg(pr.shift + co0 + c));
-                o[c] = activate(v, act, slope) * out_mul;
-            }
-        }
+        for (int c = 0; c < kGroup; ++c)
+            if (co0 + c < cout) o[c] = activate(fmaf(acc[j][c], sc[c], sh[c]), act, slope) * out_mul;
     }
 }
 
@@ -285,7 +308,7 @@ static int launch_conv(const ConvBatch &batch, int n, int cin, int cout, int H, 
     const int groups = (cout + kGroup - 1) / kGroup;
     int tiles = 1, tile_px = npix, threads = 32;
     conv_geometry(npix, groups * n, tiles, tile_px, threads);
-    const size_t smem = (size_t)kStages * ((size_t)threads * kPix * kRow4 + kWChunk4) * sizeof(float4);
+    const size_t smem = (size_t)(threads / 32) * kStages * kWarpStage4 * sizeof(float4);
     dim3 grid(tiles, groups, n);
     if (taps == 1) {
         static bool attr1 = false;
