@@ -27,7 +27,7 @@
 namespace ojdf {
 
 constexpr int kGroup = 20;          // output channels per thread (19 padded to 20 for FusionNet)
-constexpr int kPix = 4;             // pixels per thread
+constexpr int kPix = 2;             // pixels per thread
 constexpr int kMaxCT = 160;         // widest block (5 warps)
 constexpr int kKC = 8;              // channels per pipeline chunk
 constexpr int kRow4 = kKC / 4 + 1;  // float4 per staged pixel row (+1 pad: odd stride, conflict-free LDS.128)
