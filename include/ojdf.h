@@ -138,10 +138,15 @@ typedef struct ojdf_conv_problem {
     const float *scale_dev;
     const float *shift_dev;
     float *out_dev;
-    int in_stride, out_stride, out_coffset, dilation;
+    const float *residual_dev;      /* optional (H*W, residual_stride): added before the activation */
+    int in_stride, out_stride, out_coffset, dilation, residual_stride;
 } ojdf_conv_problem;
+/* act additionally accepts 4 = sigmoid.  scratch_dev (optional, scratch_bytes): when the pixel count
+ * alone cannot fill the GPU (AdapNet++'s 15x20 maps) the K loop is split across blocks, partial sums go
+ * to the scratch and a second kernel reduces them in a fixed order (deterministic). */
 int ojdf_conv_nhwc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
-                           int taps, int act, float slope, float out_mul, void *stream);
+                           int taps, int act, float slope, float out_mul, float *scratch_dev, size_t scratch_bytes,
+                           void *stream);
 /* nn.AvgPool2d(3, stride 1, padding 1) of VortexPooling (modules/model.py:114-116), C % 4 == 0. */
 int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int W, int C, float *out_dev, int out_stride,
                        void *stream);
@@ -152,6 +157,18 @@ int ojdf_vortex_bias(const float *in_dev, int in_stride, int npix, int C, const 
                      const float *g_scale_dev, const float *g_shift_dev, int Cg, const float *wf1_dev,
                      const float *f_scale_dev, const float *f_shift_dev, int Cout, float *partial_dev,
                      int partial_blocks, float *shift_out_dev, void *stream);
+/* Generalisation used by AdapNet++'s eASPP branch 5 (modules/adapnet.py:201-205): C <= 2048 and an
+ * optional ReLU on the pooled branch (v_relu). */
+int ojdf_gap_bias(const float *in_dev, int in_stride, int npix, int C, const float *wg_dev,
+                  const float *g_scale_dev, const float *g_shift_dev, int Cg, int v_relu, const float *wf1_dev,
+                  const float *f_scale_dev, const float *f_shift_dev, int Cout, float *partial_dev,
+                  int partial_blocks, float *shift_out_dev, void *stream);
+/* (C, npix) fp32 <-> pixel-major (npix, stride) with a channel offset: hand-over between NCHW tensors
+ * and the pixel-major kernels. */
+int ojdf_nchw_to_nhwc(const float *in_dev, int C, int npix, float *out_dev, int out_stride, int out_coffset,
+                      void *stream);
+int ojdf_nhwc_to_nchw(const float *in_dev, int in_stride, int in_coffset, int C, int npix, float *out_dev,
+                      void *stream);
 /* Network input assembly (modules/pipeline.py:74-102, modules/model.py:269,274): head A gets
  * [values(P) | weights(P) | last_a] (the depth frame), head B (optional) [values | weights | last_b]
  * (the normalised label frame), pixel-major with `stride` floats per pixel. */

@@ -29,9 +29,12 @@ _SIGNATURES = {
     'ojdf_integrate_updates': (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i,
                                     _vp, _sz, _vp]),
     'ojdf_conv_nhwc': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _i, _i, _vp]),
-    'ojdf_conv_nhwc_batched': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),
+    'ojdf_conv_nhwc_batched': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _sz, _vp]),
     'ojdf_avgpool3_nhwc': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     'ojdf_vortex_bias': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp]),
+    'ojdf_gap_bias': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp]),
+    'ojdf_nchw_to_nhwc': (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
+    'ojdf_nhwc_to_nchw': (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     'ojdf_pack_fusion_input': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
 }
 

@@ -35,11 +35,13 @@ constexpr int kWChunk4 = kKC * kGroup / 4;           // float4 of weights per ch
 constexpr int kStages = 3;
 constexpr int kMaxBatch = 8;
 
-enum Act { kNone = 0, kRelu = 1, kLeaky = 2, kTanh = 3 };
+enum Act { kNone = 0, kRelu = 1, kLeaky = 2, kTanh = 3, kSigmoid = 4 };
 
 struct ConvProblem {
     const float *in; const float *weights; const float *scale; const float *shift; float *out;
-    int in_stride, out_stride, out_coff, dil;
+    const float *residual;          // optional: added before the activation (ResNet shortcut), row stride res_stride
+    float *partial;                 // split-K scratch of this problem: [splits][npix][groups*kGroup]
+    int in_stride, out_stride, out_coff, dil, res_stride;
 };
 struct ConvBatch { ConvProblem p[kMaxBatch]; };
 
@@ -48,6 +50,7 @@ __device__ __forceinline__ float activate(float v, int act, float slope)
     if (act == kRelu) return v > 0.0f ? v : 0.0f;
     if (act == kLeaky) return v > 0.0f ? v : v * slope;
     if (act == kTanh) return tanhf(v);
+    if (act == kSigmoid) return 1.0f / (1.0f + expf(-v));
     return v;
 }
 
@@ -70,10 +73,12 @@ constexpr int kWarpStage4 = kWarpPix * kRow4 + kWChunk4;       // float4 per war
 
 template <int TAPS>
 __global__ void __launch_bounds__(kMaxCT, 3)
-conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, int act, float slope, float out_mul)
+conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, int act, float slope, float out_mul,
+                 int splits)
 {
     extern __shared__ float4 smem4[];
-    const ConvProblem pr = batch.p[blockIdx.z];
+    const int split = blockIdx.z % splits;
+    const ConvProblem pr = batch.p[blockIdx.z / splits];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cin8 = (cin + kKC - 1) / kKC * kKC, nk = cin8 / kKC, cin4 = (cin + 3) >> 2;
     const int g = blockIdx.y;
@@ -104,8 +109,10 @@ conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, 
         }
         s_ok[i] = m;
     }
-    const int nchunks = TAPS * nk;
-    int i_tap = 0, i_k8 = 0;                               // (tap, k8) of the next chunk to issue
+    const int nchunks_all = TAPS * nk;
+    const int ch_begin = (int)((long long)nchunks_all * split / splits);       // this block's slice of the K loop
+    const int nchunks = (int)((long long)nchunks_all * (split + 1) / splits) - ch_begin;
+    int i_tap = ch_begin / nk, i_k8 = ch_begin - (ch_begin / nk) * nk;            // (tap, k8) of the next chunk to issue
     auto issue = [&](int ch) {
         if (ch < nchunks) {
             const int dy = TAPS == 1 ? 0 : (i_tap / 3 - 1) * pr.dil, dx = TAPS == 1 ? 0 : (i_tap % 3 - 1) * pr.dil;
@@ -135,7 +142,7 @@ conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, 
         for (int c = 0; c < kGroup; ++c) acc[j][c] = 0.0f;
     const int tail = cin & 3;                          // real channels in the last float4 (0 = all four)
 
-    int k8 = 0;
+    int k8 = ch_begin % nk;
     for (int ch = 0; ch < nchunks; ++ch) {
         cp_async_wait<1>();                            // this lane's copies of chunk ch have landed
         __syncwarp();                                  // ... and every lane's; stage (ch+2)%3 is free again
@@ -175,6 +182,18 @@ conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, 
     }
     cp_async_wait<0>();
     const int co0 = g * kGroup;
+    if (splits > 1) {                                  // raw partial sums; conv_reduce_kernel finishes the layer
+        const int cpad = gridDim.y * kGroup;
+#pragma unroll
+        for (int j = 0; j < kPix; ++j) {
+            const int p = tile0 + lane + 32 * j;
+            if (p >= tile_end) continue;
+            float4 *o = reinterpret_cast<float4 *>(pr.partial + ((size_t)split * npix + p) * cpad + co0);
+#pragma unroll
+            for (int q = 0; q < kGroup / 4; ++q) o[q] = make_float4(acc[j][4 * q], acc[j][4 * q + 1], acc[j][4 * q + 2], acc[j][4 * q + 3]);
+        }
+        return;
+    }
     float sc[kGroup], sh[kGroup];
 #pragma unroll
     for (int c = 0; c < kGroup; ++c) {
@@ -187,10 +206,30 @@ conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, 
         const int p = tile0 + lane + 32 * j;
         if (p >= tile_end) continue;
         float *o = pr.out + (size_t)p * pr.out_stride + pr.out_coff + co0;
+        const float *r = pr.residual ? pr.residual + (size_t)p * pr.res_stride + co0 : nullptr;
 #pragma unroll
         for (int c = 0; c < kGroup; ++c)
-            if (co0 + c < cout) o[c] = activate(fmaf(acc[j][c], sc[c], sh[c]), act, slope) * out_mul;
+            if (co0 + c < cout) {
+                float v = fmaf(acc[j][c], sc[c], sh[c]);
+                if (r) v += r[c];
+                o[c] = activate(v, act, slope) * out_mul;
+            }
     }
+}
+
+// Second half of a split-K convolution: sum the partials in split order, then the same epilogue.
+__global__ void __launch_bounds__(256)
+conv_reduce_kernel(ConvBatch batch, int npix, int cout, int cpad, int splits, int act, float slope, float out_mul)
+{
+    const ConvProblem pr = batch.p[blockIdx.y];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)npix * cout) return;
+    const int p = (int)(i / cout), c = (int)(i - (long long)p * cout);
+    float a = 0.0f;
+    for (int s = 0; s < splits; ++s) a += pr.partial[((size_t)s * npix + p) * cpad + c];
+    float v = fmaf(a, __ldg(pr.scale + c), __ldg(pr.shift + c));
+    if (pr.residual) v += pr.residual[(size_t)p * pr.res_stride + c];
+    pr.out[(size_t)p * pr.out_stride + pr.out_coff + c] = activate(v, act, slope) * out_mul;
 }
 
 // 3x3 average pool, stride 1, zero padding counted in the divisor (nn.AvgPool2d default), NHWC.
@@ -215,46 +254,48 @@ avgpool3_kernel(const float *__restrict__ in, int in_stride, int H, int W, int C
     reinterpret_cast<float4 *>(out + (size_t)p * out_stride)[c4] = make_float4(s.x / 9.0f, s.y / 9.0f, s.z / 9.0f, s.w / 9.0f);
 }
 
-// Per-channel sums over all pixels (global average pool numerator): partial sums per block into
-// `partial` [gridDim.x][C]; the tiny second stage runs inside vortex_bias_kernel.
+// Per-channel sums over all pixels (global average pool numerator): partial sums per block row into
+// `partial` [gridDim.x][C]; the tiny second stage runs inside gap_bias_kernel.
 __global__ void __launch_bounds__(256)
 channel_sum_kernel(const float *__restrict__ in, int in_stride, int npix, int C, float *__restrict__ partial)
 {
-    // thread = channel (C <= 256), block strides over pixels
-    const int c = threadIdx.x;
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;       // thread = channel, block row strides over pixels
     if (c >= C) return;
     float s = 0.0f;
     for (int p = blockIdx.x; p < npix; p += gridDim.x) s += __ldg(in + (size_t)p * in_stride + c);
     partial[(size_t)blockIdx.x * C + c] = s;
 }
 
-// VortexPooling's global branch (modules/model.py:107-112): mean -> 1x1 conv -> (bilinear upsample
-// of a 1x1 map = constant) -> BatchNorm gives a per-channel constant v1; the `final` 1x1 conv sees it
-// as the bias  shift_out[co] = final_shift[co] + final_scale[co] * sum_c Wf[co, c] * v1[c].
+// Global-pool branch folded into a bias.  VortexPooling (modules/model.py:107-112): mean -> 1x1 conv ->
+// (bilinear upsample of a 1x1 map = constant) -> BatchNorm; eASPP branch 5 (modules/adapnet.py:201-205):
+// mean -> 1x1 conv -> ReLU -> upsample.  Either way the branch is a per-channel constant
+// v[c] = act(g_scale[c] * (wg[c,:] . mean) + g_shift[c]) and the following 1x1 conv sees it as
+// shift_out[co] = f_shift[co] + f_scale[co] * sum_c wf1[co,c] * v[c].   C <= 2048, Cg, Cout <= 256.
 __global__ void __launch_bounds__(256)
-vortex_bias_kernel(const float *__restrict__ partial, int nblocks, int npix, int C,
-                   const float *__restrict__ wg /* [Cg][C] */, const float *__restrict__ g_scale, const float *__restrict__ g_shift, int Cg,
-                   const float *__restrict__ wf1 /* [Cout][Cg] */, const float *__restrict__ f_scale, const float *__restrict__ f_shift, int Cout,
-                   float *__restrict__ shift_out)
+gap_bias_kernel(const float *__restrict__ partial, int nblocks, int npix, int C,
+                const float *__restrict__ wg /* [Cg][C] */, const float *__restrict__ g_scale, const float *__restrict__ g_shift, int Cg,
+                int v_relu, const float *__restrict__ wf1 /* [Cout][Cg] */, const float *__restrict__ f_scale,
+                const float *__restrict__ f_shift, int Cout, float *__restrict__ shift_out)
 {
-    __shared__ float s_mean[256];
-    __shared__ float s_v1[256];
+    __shared__ float s_mean[2048];
+    __shared__ float s_v[256];
     const int t = threadIdx.x;
-    if (t < C) {
+    for (int c = t; c < C; c += blockDim.x) {
         float s = 0.0f;
-        for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * C + t];
-        s_mean[t] = s / (float)npix;
+        for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * C + c];
+        s_mean[c] = s / (float)npix;
     }
     __syncthreads();
     if (t < Cg) {
         float a = 0.0f;
         for (int c = 0; c < C; ++c) a = fmaf(wg[(size_t)t * C + c], s_mean[c], a);
-        s_v1[t] = fmaf(a, g_scale[t], g_shift[t]);
+        a = fmaf(a, g_scale[t], g_shift[t]);
+        s_v[t] = v_relu ? fmaxf(a, 0.0f) : a;
     }
     __syncthreads();
     if (t < Cout) {
         float a = 0.0f;
-        for (int c = 0; c < Cg; ++c) a = fmaf(wf1[(size_t)t * Cg + c], s_v1[c], a);
+        for (int c = 0; c < Cg; ++c) a = fmaf(wf1[(size_t)t * Cg + c], s_v[c], a);
         shift_out[t] = fmaf(a, f_scale[t], f_shift[t]);
     }
 }
@@ -280,6 +321,40 @@ pack_input_kernel(const float *__restrict__ vals, const float *__restrict__ wts,
     if (b) b[2 * P] = last_b[p];
 }
 
+// (C, npix) <-> (npix, stride) fp32 transposes through a 32x33 shared tile: the hand-over between
+// the library-backed NCHW front of AdapNet++ and the pixel-major kernels.
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float *__restrict__ in, int C, int npix, float *__restrict__ out, int out_stride, int out_coff)
+{
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int c = c0 + r, p = p0 + threadIdx.x;
+        tile[r][threadIdx.x] = (c < C && p < npix) ? in[(size_t)c * npix + p] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int p = p0 + r, c = c0 + threadIdx.x;
+        if (p < npix && c < C) out[(size_t)p * out_stride + out_coff + c] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const float *__restrict__ in, int in_stride, int in_coff, int C, int npix, float *__restrict__ out)
+{
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int p = p0 + r, c = c0 + threadIdx.x;
+        tile[r][threadIdx.x] = (c < C && p < npix) ? in[(size_t)p * in_stride + in_coff + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int c = c0 + r, p = p0 + threadIdx.x;
+        if (c < C && p < npix) out[(size_t)c * npix + p] = tile[threadIdx.x][r];
+    }
+}
+
 }  // namespace ojdf
 
 using namespace ojdf;
@@ -301,23 +376,42 @@ static void conv_geometry(int npix, int blocks_per_tile, int &tiles, int &tile_p
     }
 }
 
-static int launch_conv(const ConvBatch &batch, int n, int cin, int cout, int H, int W, int taps, int act, float slope,
-                       float out_mul, cudaStream_t s)
+static int launch_conv(ConvBatch &batch, int n, int cin, int cout, int H, int W, int taps, int act, float slope,
+                       float out_mul, float *scratch, size_t scratch_bytes, cudaStream_t s)
 {
     const int npix = H * W;
-    const int groups = (cout + kGroup - 1) / kGroup;
+    const int groups = (cout + kGroup - 1) / kGroup, cpad = groups * kGroup;
+    const int nchunks = taps * ((cin + kKC - 1) / kKC);
+    // split the K loop when the pixels alone cannot fill the machine (AdapNet's 15x20 feature maps)
+    const long long warps = (long long)((npix + 32 * kPix - 1) / (32 * kPix)) * groups * n;
+    int splits = 1;
+    if (scratch && warps < 148 * 8) {
+        splits = (int)((148 * 16 + warps - 1) / warps);
+        if (splits > nchunks / 4) splits = nchunks / 4;          // keep >= 4 chunks per slice
+        if (splits > 32) splits = 32;
+        const size_t per_split = (size_t)n * npix * cpad * sizeof(float);
+        if (per_split && (size_t)splits * per_split > scratch_bytes) splits = (int)(scratch_bytes / per_split);
+        if (splits < 2) splits = 1;
+    }
+    if (splits > 1)
+        for (int i = 0; i < n; ++i) batch.p[i].partial = scratch + (size_t)i * splits * npix * cpad;
     int tiles = 1, tile_px = npix, threads = 32;
-    conv_geometry(npix, groups * n, tiles, tile_px, threads);
+    conv_geometry(npix, groups * n * splits, tiles, tile_px, threads);
     const size_t smem = (size_t)(threads / 32) * kStages * kWarpStage4 * sizeof(float4);
-    dim3 grid(tiles, groups, n);
+    dim3 grid(tiles, groups, n * splits);
     if (taps == 1) {
         static bool attr1 = false;
         if (!attr1) { cudaFuncSetAttribute(conv_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr1 = true; }
-        conv_tile_kernel<1><<<grid, threads, smem, s>>>(batch, cin, H, W, tile_px, cout, act, slope, out_mul);
+        conv_tile_kernel<1><<<grid, threads, smem, s>>>(batch, cin, H, W, tile_px, cout, act, slope, out_mul, splits);
     } else {
         static bool attr9 = false;
         if (!attr9) { cudaFuncSetAttribute(conv_tile_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr9 = true; }
-        conv_tile_kernel<9><<<grid, threads, smem, s>>>(batch, cin, H, W, tile_px, cout, act, slope, out_mul);
+        conv_tile_kernel<9><<<grid, threads, smem, s>>>(batch, cin, H, W, tile_px, cout, act, slope, out_mul, splits);
+    }
+    if (splits > 1) {
+        dim3 rgrid((unsigned)(((long long)npix * cout + 255) / 256), n);
+        conv_reduce_kernel<<<rgrid, 256, 0, s>>>(batch, npix, cout, cpad, splits, act, slope, out_mul);
+        return launched(2);
     }
     return launched(1);
 }
@@ -325,23 +419,26 @@ static int launch_conv(const ConvBatch &batch, int n, int cin, int cout, int H, 
 static bool problem_ok(const ojdf_conv_problem &q, int cin, int cout)
 {
     return q.in_dev && q.weights_dev && q.scale_dev && q.shift_dev && q.out_dev && !(q.in_stride & 3) &&
-           q.in_stride >= ((cin + 3) & ~3) && q.out_stride >= q.out_coffset + cout && q.out_coffset >= 0 && q.dilation >= 1;
+           q.in_stride >= ((cin + 3) & ~3) && q.out_stride >= q.out_coffset + cout && q.out_coffset >= 0 && q.dilation >= 1 &&
+           (!q.residual_dev || q.residual_stride >= cout);
 }
 
 extern "C" int ojdf_conv_nhwc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H,
-                                      int W, int taps, int act, float slope, float out_mul, void *stream)
+                                      int W, int taps, int act, float slope, float out_mul, float *scratch_dev,
+                                      size_t scratch_bytes, void *stream)
 {
     if (!problems_host || n_problems < 1 || n_problems > kMaxBatch || cin < 1 || cout < 1 || H < 1 || W < 1 ||
-        H > 32767 || W > 32767 || (taps != 1 && taps != 9) || act < 0 || act > 3)
+        H > 32767 || W > 32767 || (taps != 1 && taps != 9) || act < 0 || act > 4)
         return OJDF_ERR_BADARG;
     ConvBatch b;
     for (int i = 0; i < kMaxBatch; ++i) {
         const ojdf_conv_problem &q = problems_host[i < n_problems ? i : 0];
         if (i < n_problems && !problem_ok(q, cin, cout)) return OJDF_ERR_BADARG;
-        b.p[i] = ConvProblem{q.in_dev, q.weights_dev, q.scale_dev, q.shift_dev, q.out_dev, q.in_stride, q.out_stride,
-                             q.out_coffset, q.dilation};
+        b.p[i] = ConvProblem{q.in_dev, q.weights_dev, q.scale_dev, q.shift_dev, q.out_dev, q.residual_dev, nullptr,
+                             q.in_stride, q.out_stride, q.out_coffset, q.dilation, q.residual_stride};
     }
-    return launch_conv(b, n_problems, cin, cout, H, W, taps, act, slope, out_mul, (cudaStream_t)stream);
+    return launch_conv(b, n_problems, cin, cout, H, W, taps, act, slope, out_mul, scratch_dev, scratch_bytes,
+                       (cudaStream_t)stream);
 }
 
 extern "C" int ojdf_conv_nhwc(const float *in_dev, int in_stride, int cin, int H, int W, int taps, int dilation,
@@ -349,8 +446,9 @@ extern "C" int ojdf_conv_nhwc(const float *in_dev, int in_stride, int cin, int H
                               int act, float slope, float out_mul, float *out_dev, int out_stride, int out_coffset,
                               void *stream)
 {
-    ojdf_conv_problem q = {in_dev, weights_dev, scale_dev, shift_dev, out_dev, in_stride, out_stride, out_coffset, dilation};
-    return ojdf_conv_nhwc_batched(&q, 1, cin, cout, H, W, taps, act, slope, out_mul, stream);
+    ojdf_conv_problem q = {in_dev, weights_dev, scale_dev, shift_dev, out_dev, nullptr, in_stride, out_stride, out_coffset,
+                           dilation, 0};
+    return ojdf_conv_nhwc_batched(&q, 1, cin, cout, H, W, taps, act, slope, out_mul, nullptr, 0, stream);
 }
 
 extern "C" int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int W, int C, float *out_dev, int out_stride,
@@ -364,20 +462,30 @@ extern "C" int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int
     return launched(1);
 }
 
+extern "C" int ojdf_gap_bias(const float *in_dev, int in_stride, int npix, int C, const float *wg_dev,
+                             const float *g_scale_dev, const float *g_shift_dev, int Cg, int v_relu, const float *wf1_dev,
+                             const float *f_scale_dev, const float *f_shift_dev, int Cout, float *partial_dev,
+                             int partial_blocks, float *shift_out_dev, void *stream)
+{
+    if (!in_dev || !wg_dev || !g_scale_dev || !g_shift_dev || !wf1_dev || !f_scale_dev || !f_shift_dev || !partial_dev ||
+        !shift_out_dev || npix < 1 || C < 1 || C > 2048 || Cg < 1 || Cg > 256 || Cout < 1 || Cout > 256 || in_stride < C ||
+        partial_blocks < 1)
+        return OJDF_ERR_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int pb = partial_blocks < npix ? partial_blocks : npix;
+    channel_sum_kernel<<<dim3(pb, (C + 255) / 256), 256, 0, s>>>(in_dev, in_stride, npix, C, partial_dev);
+    gap_bias_kernel<<<1, 256, 0, s>>>(partial_dev, pb, npix, C, wg_dev, g_scale_dev, g_shift_dev, Cg, v_relu, wf1_dev,
+                                     f_scale_dev, f_shift_dev, Cout, shift_out_dev);
+    return launched(2);
+}
+
 extern "C" int ojdf_vortex_bias(const float *in_dev, int in_stride, int npix, int C, const float *wg_dev,
                                 const float *g_scale_dev, const float *g_shift_dev, int Cg, const float *wf1_dev,
                                 const float *f_scale_dev, const float *f_shift_dev, int Cout, float *partial_dev,
                                 int partial_blocks, float *shift_out_dev, void *stream)
 {
-    if (!in_dev || !wg_dev || !g_scale_dev || !g_shift_dev || !wf1_dev || !f_scale_dev || !f_shift_dev || !partial_dev ||
-        !shift_out_dev || npix < 1 || C < 1 || C > 256 || Cg < 1 || Cg > 256 || Cout < 1 || Cout > 256 || in_stride < C ||
-        partial_blocks < 1)
-        return OJDF_ERR_BADARG;
-    cudaStream_t s = (cudaStream_t)stream;
-    channel_sum_kernel<<<partial_blocks, 256, 0, s>>>(in_dev, in_stride, npix, C, partial_dev);
-    vortex_bias_kernel<<<1, 256, 0, s>>>(partial_dev, partial_blocks, npix, C, wg_dev, g_scale_dev, g_shift_dev, Cg, wf1_dev,
-                                        f_scale_dev, f_shift_dev, Cout, shift_out_dev);
-    return launched(2);
+    return ojdf_gap_bias(in_dev, in_stride, npix, C, wg_dev, g_scale_dev, g_shift_dev, Cg, 0, wf1_dev, f_scale_dev,
+                         f_shift_dev, Cout, partial_dev, partial_blocks, shift_out_dev, stream);
 }
 
 extern "C" int ojdf_pack_fusion_input(const float *vals_dev, const float *wts_dev, const float *last_a_dev,
@@ -389,5 +497,23 @@ extern "C" int ojdf_pack_fusion_input(const float *vals_dev, const float *wts_de
         return OJDF_ERR_BADARG;
     pack_input_kernel<<<(npix + 255) / 256, 256, 0, (cudaStream_t)stream>>>(vals_dev, wts_dev, last_a_dev, last_b_dev, npix, P,
                                                                             out_a_dev, out_b_dev, stride);
+    return launched(1);
+}
+
+extern "C" int ojdf_nchw_to_nhwc(const float *in_dev, int C, int npix, float *out_dev, int out_stride, int out_coffset,
+                                 void *stream)
+{
+    if (!in_dev || !out_dev || C < 1 || npix < 1 || out_stride < out_coffset + C || out_coffset < 0) return OJDF_ERR_BADARG;
+    nchw_to_nhwc_kernel<<<dim3((npix + 31) / 32, (C + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        in_dev, C, npix, out_dev, out_stride, out_coffset);
+    return launched(1);
+}
+
+extern "C" int ojdf_nhwc_to_nchw(const float *in_dev, int in_stride, int in_coffset, int C, int npix, float *out_dev,
+                                 void *stream)
+{
+    if (!in_dev || !out_dev || C < 1 || npix < 1 || in_stride < in_coffset + C || in_coffset < 0) return OJDF_ERR_BADARG;
+    nhwc_to_nchw_kernel<<<dim3((npix + 31) / 32, (C + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        in_dev, in_stride, in_coffset, C, npix, out_dev);
     return launched(1);
 }

@@ -85,15 +85,22 @@ class Encoder(nn.Module):
             net.layer4[i] = BottleneckSSMA(*u, downsample=down, copy_from=net.layer4[i])
         self.res_n50_enc = net
 
-    def forward(self, x):
+    def forward_front(self, x):
+        """Everything down to the first (strided) unit of layer3: returns (x at /16, skip2, skip1)."""
         n = self.res_n50_enc
         x = n.maxpool(n.relu(n.bn1(n.conv1(x))))
         x = n.layer1(x)
         s2 = self.enc_skip2_conv_bn(self.enc_skip2_conv(x))
         x = n.layer2(x)
         s1 = self.enc_skip1_conv_bn(self.enc_skip1_conv(x))
-        x = n.layer4(n.layer3(x))
-        return x, s2, s1
+        return n.layer3[0](x), s2, s1
+
+    def forward(self, x):
+        n = self.res_n50_enc
+        x, s2, s1 = self.forward_front(x)
+        for unit in list(n.layer3)[1:]:
+            x = unit(x)
+        return n.layer4(x), s2, s1
 
 
 def _aspp_branch(cin, mid, cout, rate):
@@ -200,17 +207,61 @@ class AdapNet(nn.Module):
 
     def no_resn50_dropout(self):
         """Reference helper (modules/adapnet.py:386-388): only layer3[2] of both encoders."""
+        self._engine = None
         self.encoder_mod1.res_n50_enc.layer3[2].dropout = False
         self.encoder_mod2.res_n50_enc.layer3[2].dropout = False
 
+    # ---- libojdf engine for the 15x20 tail (adapnet_engine.py); same invalidation rules as FusionNet
+    _engine = None
+    use_engine = True
+
+    def train(self, mode=True):
+        self._engine = None
+        return super().train(mode)
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    def engine_ready(self, x):
+        return self.use_engine and not self.training and not torch.is_grad_enabled() and x.is_cuda
+
+    def _tail(self, pres):
+        from .adapnet_engine import EncoderTailEngine
+        h, w = pres[0].shape[-2:]
+        e = self._engine
+        if e is None or (e.h, e.w) != (h, w) or e.device != pres[0].device:
+            encs = [self.encoder_mod1] + ([self.encoder_mod2] if self.stage != 1 else [])
+            heads = [self.eASPP] if self.stage == 1 else [self.eASPP_mod1, self.eASPP_mod2]
+            e = self._engine = EncoderTailEngine(encs, heads, h, w, pres[0].device)
+        return e.forward(pres)
+
     def set_bottleneck_dropout(self, enabled):
         """Switch the eval-time-active dropout of every multi-scale unit (deterministic runs)."""
+        self._engine = None
         for m in self.modules():
             if isinstance(m, BottleneckSSMA):
                 m.dropout = bool(enabled) and m.dropout_default
         return self
 
     def forward(self, mod1, mod2=None):
+        if self.engine_ready(mod1):
+            # front (conv1..layer3[0]) on the library, the 15x20 tail + eASPP on libojdf's kernels
+            pre1, skip2, skip1 = self.encoder_mod1.forward_front(mod1)
+            if self.stage == 1:
+                x = self._tail([pre1])[0]
+            else:
+                pre2, m2_s2, m2_s1 = self.encoder_mod2.forward_front(mod2)
+                x, x2 = self._tail([pre1, pre2])
+                skip2 = self.ssma_s2(skip2, m2_s2)
+                skip1 = self.ssma_s1(skip1, m2_s1)
+                x = self.ssma_res(x, x2)
+            aux1, aux2, res = self.decoder(x, skip1, skip2)
+            return [res, aux1, aux2]
         if self.stage == 1:
             x, skip2, skip1 = self.encoder_mod1(mod1)
             x = self.eASPP(x)

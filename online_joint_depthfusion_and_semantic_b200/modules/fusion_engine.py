@@ -22,7 +22,7 @@ from torch import nn
 from .. import _lib
 
 _GROUP = 20
-_ACT = {'none': 0, 'relu': 1, 'lrelu': 2, 'tanh': 3}
+_ACT = {'none': 0, 'relu': 1, 'lrelu': 2, 'tanh': 3, 'sigmoid': 4}
 
 
 def _pad4(c):
@@ -32,8 +32,8 @@ def _pad4(c):
 class ConvProblem(C.Structure):
     """include/ojdf.h: ojdf_conv_problem."""
     _fields_ = [('in_dev', C.c_void_p), ('weights_dev', C.c_void_p), ('scale_dev', C.c_void_p), ('shift_dev', C.c_void_p),
-                ('out_dev', C.c_void_p), ('in_stride', C.c_int), ('out_stride', C.c_int), ('out_coffset', C.c_int),
-                ('dilation', C.c_int)]
+                ('out_dev', C.c_void_p), ('residual_dev', C.c_void_p), ('in_stride', C.c_int), ('out_stride', C.c_int),
+                ('out_coffset', C.c_int), ('dilation', C.c_int), ('residual_stride', C.c_int)]
 
 
 class _Conv:
@@ -65,10 +65,11 @@ class _Conv:
         self.shift = t.float().contiguous().to(device)
         self.act, self.slope = _ACT[act], float(slope)
 
-    def problem(self, src, src_stride, dst, dst_stride, dst_off=0, shift=None):
+    def problem(self, src, src_stride, dst, dst_stride, dst_off=0, shift=None, residual=None, residual_stride=0):
         return ConvProblem(src.data_ptr(), self.weights.data_ptr(), self.scale.data_ptr(),
-                           (self.shift if shift is None else shift).data_ptr(), dst.data_ptr(), src_stride, dst_stride,
-                           dst_off, self.dil)
+                           (self.shift if shift is None else shift).data_ptr(), dst.data_ptr(),
+                           None if residual is None else residual.data_ptr(), src_stride, dst_stride, dst_off, self.dil,
+                           residual_stride)
 
 
 class _Vortex:
@@ -215,7 +216,7 @@ class FusionNetEngine:
                 if kind == 'conv':
                     _, arr, n, cin, cout, taps, act, slope = step[:8]
                     out_mul = step[8] if len(step) > 8 else 1.0
-                    _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, st))
+                    _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, None, 0, st))
                 elif kind == 'pool':
                     _, src, ss, ch, dst, ds = step
                     _lib.check(L.ojdf_avgpool3_nhwc(src.data_ptr(), ss, H, W, ch, dst.data_ptr(), ds, st))

@@ -1,0 +1,56 @@
+"""AdapNet++ with its 15x20 tail on libojdf's kernels vs the plain PyTorch fp32 forward of the same
+module (bit-identical to the reference's modules/adapnet.py on CPU, tests/test_networks_cpu.py).
+Tolerance: the north star's 1e-4 relative on the semantic logits (max |a-b| <= 1e-4 * max |b|)."""
+import pytest
+import torch
+
+from online_joint_depthfusion_and_semantic_b200.config import fusion_config
+from online_joint_depthfusion_and_semantic_b200.modules.adapnet import AdapNet
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+
+
+def _net(stage, seed=11):
+    torch.manual_seed(seed)
+    cfg = fusion_config(240, 320)
+    cfg.SEMANTIC_2D_MODEL.stage = stage
+    net = AdapNet(cfg.SEMANTIC_2D_MODEL)
+    g = torch.Generator().manual_seed(seed)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(0.1 * torch.randn(m.num_features, generator=g))
+            m.running_var.copy_(0.6 + 0.8 * torch.rand(m.num_features, generator=g))
+    net.set_bottleneck_dropout(False)
+    return net.to(DEV).eval()
+
+
+@pytest.mark.parametrize('stage,h,w', [(2, 240, 320), (1, 64, 96), (2, 48, 64)])
+def test_tail_engine_matches_torch_fp32(stage, h, w):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = _net(stage)
+    g = torch.Generator().manual_seed(3)
+    x1, x2 = torch.randn(1, 3, h, w, generator=g).to(DEV), torch.randn(1, 3, h, w, generator=g).to(DEV)
+    args = (x1, x2) if stage == 2 else (x1,)
+    with torch.no_grad():
+        net.use_engine = False
+        ref = net(*args)
+        net.use_engine = True
+        out = net(*args)
+        torch.cuda.synchronize()
+    assert net._engine is not None
+    for a, b in zip(out, ref):
+        scale = float(b.abs().max())
+        assert float((a - b).abs().max()) <= 1e-4 * scale, (float((a - b).abs().max()), scale)
+    # label agreement of the arg-max (what the pipeline integrates)
+    assert float((out[0].argmax(1) == ref[0].argmax(1)).float().mean()) > 0.999
+
+
+def test_dropout_quirk_stays_random_with_engine():
+    net = _net(2)
+    net.set_bottleneck_dropout(True)
+    x1, x2 = torch.randn(1, 3, 48, 64, device=DEV), torch.randn(1, 3, 48, 64, device=DEV)
+    with torch.no_grad():
+        a, b = net(x1, x2)[0].clone(), net(x1, x2)[0].clone()
+    assert float((a - b).abs().max()) > 0          # eval-time-active dropout, as in the reference
