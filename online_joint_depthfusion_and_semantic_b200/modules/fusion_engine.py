@@ -40,7 +40,7 @@ class _Conv:
     """One fused conv (+BN) (+activation): weights re-laid out for conv_tile_kernel."""
 
     def __init__(self, conv, bn, act, device, cin_slice=None, slope=0.01):
-        w = conv.weight.detach().double()                       # (cout, cin, kh, kw)
+        w = conv.weight.detach().double().cpu()                 # (cout, cin, kh, kw); all folding on the host in f64
         if cin_slice is not None:
             w = w[:, cin_slice[0]:cin_slice[1]]
         cout, cin, kh, kw = w.shape
@@ -54,10 +54,10 @@ class _Conv:
         for g in range(groups):
             n = min(_GROUP, cout - g * _GROUP)
             prep[g, :, :cin, :n] = wt[:, :, g * _GROUP:g * _GROUP + n]
-        bias = conv.bias.detach().double() if conv.bias is not None else torch.zeros(cout, dtype=torch.float64)
+        bias = conv.bias.detach().double().cpu() if conv.bias is not None else torch.zeros(cout, dtype=torch.float64)
         if bn is not None:
-            s = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
-            t = (bias - bn.running_mean.detach().double()) * s + bn.bias.detach().double()
+            s = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
+            t = (bias - bn.running_mean.detach().double().cpu()) * s + bn.bias.detach().double().cpu()
         else:
             s, t = torch.ones(cout, dtype=torch.float64), bias
         self.weights = prep.float().contiguous().to(device)
