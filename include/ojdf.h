@@ -147,6 +147,24 @@ typedef struct ojdf_conv_problem {
 int ojdf_conv_nhwc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
                            int taps, int act, float slope, float out_mul, float *scratch_dev, size_t scratch_bytes,
                            void *stream);
+/* ---- a10/a17 on the tensor cores: the same tap GEMM as ojdf_conv_nhwc_batched, computed by
+ * tcgen05.mma (kind::tf32, TMEM accumulators) with TMA-staged operands and a 3xTF32 split-precision
+ * product (x = hi + lo, hi*hi + lo*hi + hi*lo), i.e. fp32-grade results (~1e-6 relative).  Replaces
+ * the reference's per-layer cuDNN convolution + BatchNorm + activation launches of
+ * modules/model.py:4-283 and modules/adapnet.py:12-415.
+ * Weights must be packed with ojdf_conv_tc_pack_weights (host-side; ready-made swizzled shared-memory
+ * images [group][tap][kchunk of 32][hi|lo][npad][32]); `weights_dev` of each problem points at the
+ * packed copy.  in_dev must be 16-byte aligned with in_stride % 4 == 0; channels >= cin of the input
+ * rows are never read (TMA bounds), so a dense-block buffer can be consumed while it grows.
+ * flags: bit 0 = do not rewrite the hi tile in shared memory (rely on the hardware ignoring the low
+ * 13 mantissa bits of a tf32 operand). */
+int ojdf_conv_tc_layout(int cout, int *npad, int *groups);
+size_t ojdf_conv_tc_weight_floats(int cin, int cout, int taps);
+/* w_host: (cout, cin, taps) fp32 as in nn.Conv2d.weight (tap = ky*3 + kx); packed_host:
+ * ojdf_conv_tc_weight_floats() floats. */
+int ojdf_conv_tc_pack_weights(const float *w_host, int cin, int cout, int taps, float *packed_host);
+int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
+                         int taps, int act, float slope, float out_mul, int flags, void *stream);
 /* nn.AvgPool2d(3, stride 1, padding 1) of VortexPooling (modules/model.py:114-116), C % 4 == 0. */
 int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int W, int C, float *out_dev, int out_stride,
                        void *stream);

@@ -1,0 +1,103 @@
+"""Bring-up / regression probe for the tcgen05 tap-GEMM (csrc/ojdf_conv_tc.cu): each case runs in its own
+process (a trapped kernel must not take the others down), compares with an fp64 torch convolution and
+prints one line.  Usage on the GPU box:  python tools/tc_probe.py [--time]"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+# (name, H, W, cin, cout, taps, dil, in_stride, out_stride, out_coff, act, residual, n_problems, flags)
+CASES = [
+    ('1x1 one tile one chunk', 8, 16, 32, 32, 1, 1, 32, 32, 0, 0, False, 1, 0),
+    ('1x1 one tile, hw-truncation flag', 8, 16, 32, 32, 1, 1, 32, 32, 0, 0, False, 1, 1),
+    ('1x1 cin 19 of stride 116', 8, 16, 19, 19, 1, 1, 116, 20, 0, 2, False, 1, 0),
+    ('1x1 4 chunks', 16, 32, 114, 114, 1, 1, 116, 116, 0, 1, False, 1, 0),
+    ('3x3 one tile', 8, 16, 32, 32, 9, 1, 32, 32, 0, 0, False, 1, 0),
+    ('3x3 dense block', 48, 64, 95, 19, 9, 1, 116, 116, 95, 2, False, 2, 0),
+    ('3x3 dil 3 ragged image', 37, 53, 19, 19, 9, 3, 20, 20, 0, 1, False, 4, 0),
+    ('3x3 dil 27', 48, 64, 19, 19, 9, 27, 20, 20, 0, 1, False, 8, 0),
+    ('1x1 570 -> 114', 48, 64, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 0),
+    ('1x1 -> 9 tanh', 48, 64, 19, 9, 1, 1, 116, 9, 0, 3, False, 1, 0),
+    ('1x1 256 out (2 groups) residual sigmoid', 30, 40, 256, 256, 1, 1, 256, 256, 0, 4, True, 1, 0),
+    ('3x3 240x320 dense block', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 0),
+]
+
+
+def run_case(idx, timing):
+    import numpy as np
+    import torch
+    from online_joint_depthfusion_and_semantic_b200 import _lib
+    from online_joint_depthfusion_and_semantic_b200.modules.fusion_engine import ConvProblem
+    name, H, W, cin, cout, taps, dil, istr, ostr, ocoff, act, use_res, nprob, flags = CASES[idx]
+    dev = torch.device('cuda:0')
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(100 + idx)
+    k = 3 if taps == 9 else 1
+    keep, probs, refs, outs = [], [], [], []
+    for i in range(nprob):
+        x = torch.randn(H * W, istr, generator=g)                           # channels >= cin are garbage on purpose
+        w = torch.randn(cout, cin, k, k, generator=g) / (cin * taps) ** 0.5
+        sc, sh = 0.5 + torch.rand(cout, generator=g), 0.1 * torch.randn(cout, generator=g)
+        res = torch.randn(H * W, cout, generator=g) if use_res else None
+        n = L.ojdf_conv_tc_weight_floats(cin, cout, taps)
+        packed = np.zeros(n, np.float32)
+        wc = np.ascontiguousarray(w.numpy().reshape(cout, cin, taps))
+        _lib.check(L.ojdf_conv_tc_pack_weights(wc.ctypes.data, cin, cout, taps, packed.ctypes.data))
+        d = dil if nprob == 1 else max(1, dil - i % 2) if taps == 9 else 1
+        xin = x[:, :cin].double().t().reshape(1, cin, H, W)
+        y = torch.nn.functional.conv2d(xin, w.double(), padding=d * (k // 2), dilation=d)[0].reshape(cout, H * W).t()
+        y = y * sc.double() + sh.double()
+        if use_res:
+            y = y + res.double()
+        y = {0: y, 1: y.clamp(min=0), 2: torch.where(y > 0, y, 0.01 * y), 3: torch.tanh(y), 4: torch.sigmoid(y)}[act]
+        out = torch.full((H * W, ostr), 7.0, device=dev)
+        t = [x.to(dev), torch.from_numpy(packed).to(dev), sc.to(dev), sh.to(dev), out, res.to(dev) if use_res else None]
+        keep.append(t)
+        probs.append(ConvProblem(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), out.data_ptr(),
+                                 t[5].data_ptr() if use_res else None, istr, ostr, ocoff, d, cout if use_res else 0))
+        refs.append(y)
+        outs.append(out)
+    arr = (ConvProblem * nprob)(*probs)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.ojdf_conv_tc_batched(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, flags, st))
+    torch.cuda.synchronize()
+    worst = 0.0
+    for y, out in zip(refs, outs):
+        o = out.cpu().double()
+        got = o[:, ocoff:ocoff + cout]
+        err = float((got - y).abs().max() / y.abs().max())
+        worst = max(worst, err)
+        untouched = torch.cat([o[:, :ocoff], o[:, ocoff + cout:]], 1)
+        if untouched.numel() and not bool((untouched == 7.0).all()):
+            worst = float('inf')
+    line = '%-44s rel.err %.3e  %s' % (name, worst, 'OK' if worst < 2e-5 else 'FAIL')
+    if timing:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            L.ojdf_conv_tc_batched(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, flags, st)
+        a.record()
+        for _ in range(20):
+            L.ojdf_conv_tc_batched(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, flags, st)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 20
+        line += '  %.1f us  %.1f TFLOP/s (fp32-equivalent)' % (ms * 1e3, 2.0 * H * W * cin * cout * taps * nprob / ms / 1e9)
+    print(line, flush=True)
+
+
+if __name__ == '__main__':
+    timing = '--time' in sys.argv
+    if '--case' in sys.argv:
+        run_case(int(sys.argv[sys.argv.index('--case') + 1]), timing)
+    else:
+        for i in range(len(CASES)):
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), '--case', str(i)] + (['--time'] if timing else []),
+                                   capture_output=True, text=True, timeout=180)
+                tail = (r.stdout + r.stderr).strip().splitlines()
+                print('\n'.join(tail[-4:]) if r.returncode else r.stdout.strip(), flush=True)
+            except subprocess.TimeoutExpired:
+                print('%-44s TIMEOUT' % CASES[i][0], flush=True)
