@@ -165,6 +165,13 @@ size_t ojdf_conv_tc_weight_floats(int cin, int cout, int taps);
 int ojdf_conv_tc_pack_weights(const float *w_host, int cin, int cout, int taps, float *packed_host);
 int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
                          int taps, int act, float slope, float out_mul, int flags, void *stream);
+/* Second generation of the same operation (csrc/ojdf_conv_tc2.cu): persistent CTAs, one TMA halo box per
+ * K chunk serving all 9 taps, A operand split into hi/lo in registers and kept in tensor memory, weight
+ * stages shared by up to 4 M-tiles, double-buffered TMEM accumulators, TMA-store epilogue.  Same
+ * arguments and packed weights as ojdf_conv_tc_batched.  flags (experiments): 2 = one M-tile per group,
+ * 4 = never use halo boxes, 8 = plain stores instead of TMA stores. */
+int ojdf_conv_tc2_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
+                          int taps, int act, float slope, float out_mul, int flags, void *stream);
 /* nn.AvgPool2d(3, stride 1, padding 1) of VortexPooling (modules/model.py:114-116), C % 4 == 0. */
 int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int W, int C, float *out_dev, int out_stride,
                        void *stream);

@@ -14,11 +14,16 @@ bottleneck dropout of the reference (modules/adapnet.py:80-82) is applied betwee
 torch's own dropout, so its random stream is the library's in both paths.
 Eval mode + no_grad only; rebuilt when parameters may have changed (same rules as FusionNetEngine).
 """
+import functools
+
 import torch
 from torch.nn import functional as F
 
 from .. import _lib
-from .fusion_engine import ConvProblem, _Conv, _pad4
+
+from .fusion_engine import ConvProblem, _Conv as _ConvBase, _pad4
+
+_Conv = functools.partial(_ConvBase, tc=False)        # this engine still runs the fp32 FMA kernels
 
 
 class _Unit:

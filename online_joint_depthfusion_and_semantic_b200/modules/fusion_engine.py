@@ -15,7 +15,9 @@ Only used in eval mode under torch.no_grad(); training (autograd through FusionN
 the module's own torch forward.  The plan is rebuilt when parameters or buffers change.
 """
 import ctypes as C
+import os
 
+import numpy as np
 import torch
 from torch import nn
 
@@ -29,6 +31,24 @@ def _pad4(c):
     return (c + 3) // 4 * 4
 
 
+def conv_mode():
+    """'tc' (default): tcgen05 3xTF32 tap GEMM (csrc/ojdf_conv_tc.cu); 'fma': the fp32 FMA kernels."""
+    m = os.environ.get('OJDF_CONV', 'tc')
+    assert m in ('tc', 'fma'), m
+    return m
+
+
+def pack_tc_weights(w):
+    """(cout, cin, kh, kw) f64/f32 host tensor -> packed float32 image for ojdf_conv_tc_batched."""
+    cout, cin, kh, kw = w.shape
+    taps = kh * kw
+    L = _lib.lib()
+    src = np.ascontiguousarray(w.float().numpy().reshape(cout, cin, taps))
+    out = np.zeros(L.ojdf_conv_tc_weight_floats(cin, cout, taps), np.float32)
+    _lib.check(L.ojdf_conv_tc_pack_weights(src.ctypes.data, cin, cout, taps, out.ctypes.data))
+    return torch.from_numpy(out)
+
+
 class ConvProblem(C.Structure):
     """include/ojdf.h: ojdf_conv_problem."""
     _fields_ = [('in_dev', C.c_void_p), ('weights_dev', C.c_void_p), ('scale_dev', C.c_void_p), ('shift_dev', C.c_void_p),
@@ -39,7 +59,7 @@ class ConvProblem(C.Structure):
 class _Conv:
     """One fused conv (+BN) (+activation): weights re-laid out for conv_tile_kernel."""
 
-    def __init__(self, conv, bn, act, device, cin_slice=None, slope=0.01):
+    def __init__(self, conv, bn, act, device, cin_slice=None, slope=0.01, tc=None):
         w = conv.weight.detach().double().cpu()                 # (cout, cin, kh, kw); all folding on the host in f64
         if cin_slice is not None:
             w = w[:, cin_slice[0]:cin_slice[1]]
@@ -61,12 +81,14 @@ class _Conv:
         else:
             s, t = torch.ones(cout, dtype=torch.float64), bias
         self.weights = prep.float().contiguous().to(device)
+        self.weights_tc = pack_tc_weights(w).to(device) if (conv_mode() == 'tc' if tc is None else tc) else None
         self.scale = s.float().contiguous().to(device)
         self.shift = t.float().contiguous().to(device)
         self.act, self.slope = _ACT[act], float(slope)
 
     def problem(self, src, src_stride, dst, dst_stride, dst_off=0, shift=None, residual=None, residual_stride=0):
-        return ConvProblem(src.data_ptr(), self.weights.data_ptr(), self.scale.data_ptr(),
+        wts = self.weights_tc if self.weights_tc is not None else self.weights
+        return ConvProblem(src.data_ptr(), wts.data_ptr(), self.scale.data_ptr(),
                            (self.shift if shift is None else shift).data_ptr(), dst.data_ptr(),
                            None if residual is None else residual.data_ptr(), src_stride, dst_stride, dst_off, self.dil,
                            residual_stride)
@@ -129,6 +151,7 @@ class FusionNetEngine:
         self._keep = [heads, tail]                              # owns every device tensor the plan points at
         self.partial = torch.empty(self.PARTIAL_BLOCKS * 256, dtype=torch.float32, device=dev)
         self.plan = []
+        self.tc = conv_mode() == 'tc'
 
         def conv_step(convs_problems):
             """convs_problems: list of (conv, problem) with identical shapes -> one batched launch."""
@@ -216,7 +239,10 @@ class FusionNetEngine:
                 if kind == 'conv':
                     _, arr, n, cin, cout, taps, act, slope = step[:8]
                     out_mul = step[8] if len(step) > 8 else 1.0
-                    _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, None, 0, st))
+                    if self.tc:
+                        _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, 0, st))
+                    else:
+                        _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, None, 0, st))
                 elif kind == 'pool':
                     _, src, ss, ch, dst, ds = step
                     _lib.check(L.ojdf_avgpool3_nhwc(src.data_ptr(), ss, H, W, ch, dst.data_ptr(), ds, st))

@@ -23,7 +23,46 @@ CASES = [
     ('1x1 -> 9 tanh', 48, 64, 19, 9, 1, 1, 116, 9, 0, 3, False, 1, 0),
     ('1x1 256 out (2 groups) residual sigmoid', 30, 40, 256, 256, 1, 1, 256, 256, 0, 4, True, 1, 0),
     ('3x3 240x320 dense block', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 0),
+    ('3x3 240x320 19->19', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 0),
+    ('1x1 240x320 456->114', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 0),
+    ('1x1 240x320 114->95', 240, 320, 114, 95, 1, 1, 116, 116, 0, 2, False, 1, 0),
+    ('1x1 240x320 19->19 into 456', 240, 320, 19, 19, 1, 1, 20, 456, 57, 1, False, 8, 0),
+    ('3x3 60x80 64->64 dil 2 residual', 60, 80, 64, 64, 9, 2, 64, 64, 0, 1, True, 2, 0),
+    ('3x3 15x20 512->512 (4 groups)', 15, 20, 512, 512, 9, 1, 512, 512, 0, 1, False, 1, 0),
+    ('3x3 30x40 64->64 dil 2 halo', 30, 40, 64, 64, 9, 2, 64, 64, 0, 1, False, 1, 0),
+    ('3x3 dense block, per-tap boxes', 48, 64, 95, 19, 9, 1, 116, 116, 95, 2, False, 2, 4),
+    ('3x3 dense block, MT=1', 48, 64, 95, 19, 9, 1, 116, 116, 95, 2, False, 2, 2),
+    ('3x3 dense block, plain stores', 48, 64, 95, 19, 9, 1, 116, 116, 95, 2, False, 2, 8),
+    ('1x1 aligned TMA store 20 of 24 at 4', 48, 64, 64, 20, 1, 1, 64, 28, 4, 1, False, 2, 0),
+    ('T: dense 240x320 no MMA', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 16),
+    ('T: dense 240x320 no split', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 32),
+    ('T: dense 240x320 no MMA no split', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 48),
+    ('T: dense 240x320 1xTF32', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 64),
+    ('T: dense 240x320 MT=1', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 2),
+    ('T: 456->114 no MMA', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 16),
+    ('T: 456->114 no split', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 32),
+    ('T: 456->114 no MMA no split', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 48),
+    ('T: 456->114 1xTF32', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 64),
+    ('P: dense', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 128),
+    ('P: dense no MMA no split', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 128 | 48),
+    ('P: 456->114', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128),
+    ('P: 456->114 no MMA no split', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 48),
+    ('P: 19->19 3x3', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 128),
+    ('P: 114->95', 240, 320, 114, 95, 1, 1, 116, 116, 0, 2, False, 1, 128),
+    ('X: dense neither', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 48),
+    ('X: dense neither, arrive not commit', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 48 | 256),
+    ('X: dense neither, no fence', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 48 | 512),
+    ('X: dense neither, arrive, no fence', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 48 | 768),
+    ('X: dense neither, plain stores', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 48 | 8),
+    ('X: dense no split', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 32),
+    ('X: dense no MMA', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 16),
+    ('X: 456 neither', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 48),
+    ('X: 456 neither plain stores', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 48 | 8),
+    ('X: 456 neither MT=1', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 48 | 2),
+    ('X: 456->112 (TMA store)', 240, 320, 456, 112, 1, 1, 456, 116, 0, 0, False, 2, 0),
+    ('X: 456->112 neither (TMA store)', 240, 320, 456, 112, 1, 1, 456, 116, 0, 0, False, 2, 48),
 ]
+FN = 'ojdf_conv_tc2_batched' if '--v1' not in sys.argv else 'ojdf_conv_tc_batched'
 
 
 def run_case(idx, timing):
@@ -62,7 +101,7 @@ def run_case(idx, timing):
         outs.append(out)
     arr = (ConvProblem * nprob)(*probs)
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(L.ojdf_conv_tc_batched(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, flags, st))
+    _lib.check(getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, flags, st))
     torch.cuda.synchronize()
     worst = 0.0
     for y, out in zip(refs, outs):
@@ -73,19 +112,30 @@ def run_case(idx, timing):
         untouched = torch.cat([o[:, :ocoff], o[:, ocoff + cout:]], 1)
         if untouched.numel() and not bool((untouched == 7.0).all()):
             worst = float('inf')
-    line = '%-44s rel.err %.3e  %s' % (name, worst, 'OK' if worst < 2e-5 else 'FAIL')
+    line = '%-44s rel.err %.3e  %s' % (name, worst, 'OK' if worst < 5e-5 else 'FAIL')
     if timing:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(3):
-            L.ojdf_conv_tc_batched(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, flags, st)
+            getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, flags, st)
         a.record()
         for _ in range(20):
-            L.ojdf_conv_tc_batched(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, flags, st)
+            getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, flags, st)
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 20
         line += '  %.1f us  %.1f TFLOP/s (fp32-equivalent)' % (ms * 1e3, 2.0 * H * W * cin * cout * taps * nprob / ms / 1e9)
     print(line, flush=True)
+    if flags & 128:
+        prof = (C.c_longlong * 32)()
+        L.ojdf_conv_tc2_profile.argtypes = [C.c_void_p]
+        L.ojdf_conv_tc2_profile(prof)                        # discard what the earlier launches accumulated
+        getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, flags, st)
+        torch.cuda.synchronize()
+        L.ojdf_conv_tc2_profile(prof)
+        p = list(prof)
+        print('   block 0 cycles: producer total %d (wait src_empty %d, b_empty %d) | mma total %d (acc_empty %d, b_full %d, a_full %d) | '
+              'split0 total %d (src_full %d, a_empty %d) | split1 total %d (src_full %d, a_empty %d) | epilogue total %d (acc_full %d)'
+              % (p[2], p[0], p[1], p[6], p[3], p[4], p[5], p[9], p[7], p[8], p[12], p[10], p[11], p[14], p[13]), flush=True)
 
 
 if __name__ == '__main__':
@@ -93,9 +143,12 @@ if __name__ == '__main__':
     if '--case' in sys.argv:
         run_case(int(sys.argv[sys.argv.index('--case') + 1]), timing)
     else:
+        only = sys.argv[sys.argv.index('--only') + 1] if '--only' in sys.argv else ''
         for i in range(len(CASES)):
+            if not CASES[i][0].startswith(only):
+                continue
             try:
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), '--case', str(i)] + (['--time'] if timing else []),
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), '--case', str(i)] + [a for a in ('--time', '--v1') if a in sys.argv],
                                    capture_output=True, text=True, timeout=180)
                 tail = (r.stdout + r.stderr).strip().splitlines()
                 print('\n'.join(tail[-4:]) if r.returncode else r.stdout.strip(), flush=True)
