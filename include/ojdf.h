@@ -168,8 +168,10 @@ int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int n_problems,
 /* Second generation of the same operation (csrc/ojdf_conv_tc2.cu): persistent CTAs, one TMA halo box per
  * K chunk serving all 9 taps, A operand split into hi/lo in registers and kept in tensor memory, weight
  * stages shared by up to 4 M-tiles, double-buffered TMEM accumulators, TMA-store epilogue.  Same
- * arguments and packed weights as ojdf_conv_tc_batched.  flags (experiments): 2 = one M-tile per group,
- * 4 = never use halo boxes, 8 = plain stores instead of TMA stores. */
+ * arguments and packed weights as ojdf_conv_tc_batched.  flags: 1 = the caller owns the pad channels
+ * [coff+cout, coff+round_up(cout,4)) of the output rows (they receive zeros; lets a width that is not a
+ * multiple of 4 use the TMA-store epilogue); experiments: 2 = one M-tile per group, 4 = never use halo boxes,
+ * 8 = plain stores instead of TMA stores, 16..512 / bits 12-15 = timing probes (see the source). */
 int ojdf_conv_tc2_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
                           int taps, int act, float slope, float out_mul, int flags, void *stream);
 /* nn.AvgPool2d(3, stride 1, padding 1) of VortexPooling (modules/model.py:114-116), C % 4 == 0. */

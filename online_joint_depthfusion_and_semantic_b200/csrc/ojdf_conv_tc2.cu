@@ -716,7 +716,10 @@ extern "C" int ojdf_conv_tc2_batched(const ojdf_conv_problem *problems_host, int
             ((uintptr_t)q.in_dev & 15) || ((uintptr_t)q.weights_dev & 15) || q.out_stride < q.out_coffset + cout ||
             q.out_coffset < 0 || q.dilation < 1 || (q.residual_dev && q.residual_stride < cout))
             return OJDF_ERR_BADARG;
-        if (prm.store_mode == 0 && ((q.out_stride & 3) || ((uintptr_t)q.out_dev & 15) || (q.out_coffset & 3) || (cout & 3)))
+        // TMA stores move whole 16-byte units: the channel offset must be a multiple of 4 and a width that is not
+        // is rounded up -- allowed only when the caller owns those pad channels (flag 1); they receive zeros
+        if (prm.store_mode == 0 && ((q.out_stride & 3) || ((uintptr_t)q.out_dev & 15) || (q.out_coffset & 3) ||
+                                    ((cout & 3) && (!(flags & 1) || q.out_coffset + ((cout + 3) & ~3) > q.out_stride))))
             prm.store_mode = 1;
     }
     for (int i = 0; i < n_problems; ++i) {
@@ -724,7 +727,7 @@ extern "C" int ojdf_conv_tc2_batched(const ojdf_conv_problem *problems_host, int
         int r = tc2::pixel_map(q.in_dev, cin, q.in_stride, H, W, prm.bwid, prm.sub_rows, &prm.in_map[i]);
         if (r) return r;
         if (prm.store_mode == 0) {
-            r = tc2::pixel_map(q.out_dev, q.out_coffset + cout, q.out_stride, H, W, tc2::kBW, tc2::kBH, &prm.out_map[i]);
+            r = tc2::pixel_map(q.out_dev, q.out_coffset + ((cout + 3) & ~3), q.out_stride, H, W, tc2::kBW, tc2::kBH, &prm.out_map[i]);
             if (r) return r;
         }
         prm.p[i] = tc2::Problem{q.weights_dev, q.scale_dev, q.shift_dev, q.out_dev, q.residual_dev,

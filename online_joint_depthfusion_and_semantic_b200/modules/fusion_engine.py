@@ -11,6 +11,10 @@ test_fusion.py:63-65); this class turns them into a launch plan over pixel-major
   * Pred chain (modules/model.py:24-52) ends in tanh * output_scale and writes (N, n_points) f32 --
     exactly the layout the integrator consumes, so no NCHW<->NHWC permutes exist anywhere.
 
+Channel groups are padded to a multiple of 4 channels inside the buffers (19 -> 20, 114 -> 116): every
+concatenation offset is then 16-byte aligned, which is what the tensor-core kernel's TMA-store epilogue
+needs; the consumers' weights carry zero rows at the pad positions (`cin_map`).
+
 Only used in eval mode under torch.no_grad(); training (autograd through FusionNet, row a2) keeps
 the module's own torch forward.  The plan is rebuilt when parameters or buffers change.
 """
@@ -29,6 +33,12 @@ _ACT = {'none': 0, 'relu': 1, 'lrelu': 2, 'tanh': 3, 'sigmoid': 4}
 
 def _pad4(c):
     return (c + 3) // 4 * 4
+
+
+def group_map(n_groups, width):
+    """Positions of n_groups x width real channels when every group is padded to a multiple of 4."""
+    pitch = _pad4(width)
+    return [g * pitch + c for g in range(n_groups) for c in range(width)], n_groups * pitch
 
 
 def conv_mode():
@@ -59,10 +69,16 @@ class ConvProblem(C.Structure):
 class _Conv:
     """One fused conv (+BN) (+activation): weights re-laid out for conv_tile_kernel."""
 
-    def __init__(self, conv, bn, act, device, cin_slice=None, slope=0.01, tc=None):
+    def __init__(self, conv, bn, act, device, cin_slice=None, slope=0.01, tc=None, cin_map=None):
         w = conv.weight.detach().double().cpu()                 # (cout, cin, kh, kw); all folding on the host in f64
         if cin_slice is not None:
             w = w[:, cin_slice[0]:cin_slice[1]]
+        if cin_map is not None:                                 # real input channel i sits at position cin_map[0][i] of
+            pos, width = cin_map                                # a `width`-channel padded buffer; pads get zero weights
+            assert len(pos) == w.shape[1]
+            wp = torch.zeros(w.shape[0], width, w.shape[2], w.shape[3], dtype=torch.float64)
+            wp[:, torch.as_tensor(pos, dtype=torch.long)] = w
+            w = wp
         cout, cin, kh, kw = w.shape
         assert kh == kw and kh in (1, 3)
         self.taps, self.cin, self.cout = kh * kw, cin, cout
@@ -95,16 +111,21 @@ class _Conv:
 
 
 class _Vortex:
-    def __init__(self, m, device):
+    def __init__(self, m, device, in_map):
+        """in_map = (positions, padded width) of the module's input channels in the source buffer."""
         gp_conv, gp_bn = m.gave_pool[1], m.gave_pool[3]
-        self.cin, self.cout = gp_conv.in_channels, gp_conv.out_channels
-        self.branches = [[_Conv(br[0], br[1], 'relu', device), _Conv(br[3], br[4], 'relu', device),
+        self.cout = gp_conv.out_channels
+        self.cin = in_map[1]                                    # padded input width
+        self.branches = [[_Conv(br[0], br[1], 'relu', device, cin_map=in_map), _Conv(br[3], br[4], 'relu', device),
                           _Conv(br[6], br[7], 'relu', device), _Conv(br[9], br[10], 'relu', device)] for br in m.branches]
         fin_conv, fin_bn = m.final[0], m.final[1]
         C_ = self.cout
-        self.final = _Conv(fin_conv, fin_bn, 'none', device, cin_slice=(C_, 5 * C_))     # the 4 branch outputs
+        # the 4 branch outputs, each in its own 4-aligned group of the branch buffer
+        self.final = _Conv(fin_conv, fin_bn, 'none', device, cin_slice=(C_, 5 * C_), cin_map=group_map(4, C_))
         # global branch: v1 = BN(conv(mean)); its share of the final conv becomes a bias
-        self.wg = gp_conv.weight.detach().reshape(C_, self.cin).float().contiguous().to(device)
+        wg = torch.zeros(C_, self.cin, dtype=torch.float32)
+        wg[:, torch.as_tensor(in_map[0], dtype=torch.long)] = gp_conv.weight.detach().reshape(C_, -1).float().cpu()
+        self.wg = wg.contiguous().to(device)
         gb = gp_conv.bias.detach().double()
         gs = gp_bn.weight.detach().double() / torch.sqrt(gp_bn.running_var.detach().double() + gp_bn.eps)
         self.g_scale = gs.float().to(device)
@@ -128,24 +149,30 @@ class FusionNetEngine:
         if not self.v3 and self.use_sem:
             raise NotImplementedError('FusionNet_v2 with a semantic input channel: use the torch forward')
 
-        def blocks(ml):
-            return [(_Conv(b.block[0], b.block[1], 'lrelu', dev), _Conv(b.block[4], b.block[5], 'lrelu', dev)) for b in ml]
+        G = _pad4(nch)                                          # pitch of one 19-channel group: 20
+        Cc = nch * (gf + 1)                                     # 114 real channels after the dense blocks
+        Cd = (gf + 1) * G                                       # ... living in 6 groups of 20 = 120 buffer channels
+        Cs, mid_s = _pad4(Cc), G                                # 116: pitch of a 114-channel group
+        self.C, self.Cs, self.Cd = Cc, Cs, Cd
 
-        Cc = nch * (gf + 1)                                     # 114
-        Cs, mid_s = _pad4(Cc), _pad4(nch)
-        self.C, self.Cs = Cc, Cs
+        def blocks(ml):
+            return [(_Conv(b.block[0], b.block[1], 'lrelu', dev, cin_map=group_map(bi + 1, nch)),
+                     _Conv(b.block[4], b.block[5], 'lrelu', dev)) for bi, b in enumerate(ml)]
+
         z = lambda c: torch.zeros(N, c, dtype=torch.float32, device=dev)     # noqa: E731
+        dense_map = group_map(gf + 1, nch)
         if self.v3:
-            heads = [(blocks(net.block0), _Vortex(net.vortex0, dev))]
+            heads = [(blocks(net.block0), _Vortex(net.vortex0, dev, dense_map))]
             if self.use_sem:
-                heads.append((blocks(net.block2), _Vortex(net.vortex2, dev)))
-            tail = _Vortex(net.vortex3, dev)
+                heads.append((blocks(net.block2), _Vortex(net.vortex2, dev, dense_map)))
+            nh = len(heads)
+            tail = _Vortex(net.vortex3, dev, group_map(nh, Cc))
         else:
-            heads, tail = [(blocks(net.block), _Vortex(net.vortex, dev))], _Vortex(net.vortex_final, dev)
-        nh = len(heads)
+            heads, nh = [(blocks(net.block), _Vortex(net.vortex, dev, dense_map))], 1
+            tail = _Vortex(net.vortex_final, dev, group_map(1, Cc))
         self.two = nh == 2
-        self.in_bufs = [z(Cs) for _ in range(nh)]
-        cat_stride = _pad4(nh * Cc) if self.v3 else Cs
+        self.in_bufs = [z(Cd) for _ in range(nh)]
+        cat_stride = nh * Cs
         self.cat = z(cat_stride)
         self.est = torch.empty(1, N, self.P, dtype=torch.float32, device=dev)
         self._keep = [heads, tail]                              # owns every device tensor the plan points at
@@ -159,22 +186,22 @@ class FusionNetEngine:
             arr = (ConvProblem * len(convs_problems))(*[p for _, p in convs_problems])
             self.plan.append(('conv', arr, len(convs_problems), c0.cin, c0.cout, c0.taps, c0.act, c0.slope))
 
-        # dense blocks, heads in lock step
+        # dense blocks, heads in lock step; block bi reads groups 0..bi and appends group bi+1
         t19 = [z(mid_s) for _ in range(nh)]
         self._keep.append(t19)
         for bi in range(gf):
-            conv_step([(heads[hh][0][bi][0], heads[hh][0][bi][0].problem(self.in_bufs[hh], Cs, t19[hh], mid_s)) for hh in range(nh)])
-            conv_step([(heads[hh][0][bi][1], heads[hh][0][bi][1].problem(t19[hh], mid_s, self.in_bufs[hh], Cs, (bi + 1) * nch))
+            conv_step([(heads[hh][0][bi][0], heads[hh][0][bi][0].problem(self.in_bufs[hh], Cd, t19[hh], mid_s)) for hh in range(nh)])
+            conv_step([(heads[hh][0][bi][1], heads[hh][0][bi][1].problem(t19[hh], mid_s, self.in_bufs[hh], Cd, (bi + 1) * G))
                        for hh in range(nh)])
 
         def vortex_steps(vs, srcs, src_stride, dsts):
             """vs: vortex modules run in lock step; srcs[i] -> dsts[i] = (buffer, stride, channel offset)."""
             n = len(vs)
             cin, Cv = vs[0].cin, vs[0].cout
-            ps = _pad4(cin)
+            ps, Cvp = _pad4(cin), _pad4(Cv)
             pools = [[z(ps) for _ in range(3)] for _ in range(n)]
             tb = [[[z(mid_s) for _ in range(2)] for _ in range(4)] for _ in range(n)]
-            br_out = [z(4 * Cv) for _ in range(n)]
+            br_out = [z(4 * Cvp) for _ in range(n)]
             self._keep += [pools, tb, br_out]
             for i, v in enumerate(vs):
                 self.plan.append(('bias', v, srcs[i], src_stride))
@@ -189,12 +216,12 @@ class FusionNetEngine:
                        for i in range(n) for b in range(4)])
             conv_step([(vs[i].branches[b][2], vs[i].branches[b][2].problem(tb[i][b][1], mid_s, tb[i][b][0], mid_s))
                        for i in range(n) for b in range(4)])
-            conv_step([(vs[i].branches[b][3], vs[i].branches[b][3].problem(tb[i][b][0], mid_s, br_out[i], 4 * Cv, b * Cv))
+            conv_step([(vs[i].branches[b][3], vs[i].branches[b][3].problem(tb[i][b][0], mid_s, br_out[i], 4 * Cvp, b * Cvp))
                        for i in range(n) for b in range(4)])
-            conv_step([(vs[i].final, vs[i].final.problem(br_out[i], 4 * Cv, dsts[i][0], dsts[i][1], dsts[i][2],
+            conv_step([(vs[i].final, vs[i].final.problem(br_out[i], 4 * Cvp, dsts[i][0], dsts[i][1], dsts[i][2],
                                                          shift=vs[i].frame_shift)) for i in range(n)])
 
-        vortex_steps([hv[1] for hv in heads], self.in_bufs, Cs, [(self.cat, cat_stride, hh * Cc) for hh in range(nh)])
+        vortex_steps([hv[1] for hv in heads], self.in_bufs, Cd, [(self.cat, cat_stride, hh * Cs) for hh in range(nh)])
         vout = z(Cs)
         self._keep.append(vout)
         vortex_steps([tail], [self.cat], cat_stride, [(vout, Cs, 0)])
@@ -233,14 +260,14 @@ class FusionNetEngine:
             st = _lib.stream_ptr(dev)
             _lib.check(L.ojdf_pack_fusion_input(vals.data_ptr(), wts.data_ptr(), frame.data_ptr(),
                                                 sem_frame.data_ptr() if self.two else None, N, P, self.in_bufs[0].data_ptr(),
-                                                self.in_bufs[1].data_ptr() if self.two else None, self.Cs, st))
+                                                self.in_bufs[1].data_ptr() if self.two else None, self.Cd, st))
             for step in self.plan:
                 kind = step[0]
                 if kind == 'conv':
                     _, arr, n, cin, cout, taps, act, slope = step[:8]
                     out_mul = step[8] if len(step) > 8 else 1.0
                     if self.tc:
-                        _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, 0, st))
+                        _lib.check(L.ojdf_conv_tc2_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, 1, st))   # 1: pads are ours
                     else:
                         _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, None, 0, st))
                 elif kind == 'pool':
