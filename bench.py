@@ -14,8 +14,12 @@ rotated every frame so the voxel working set exceeds L2), no data-path collectiv
   value  = frames/s with the frame tensors already resident in HBM
   e2e    = frames/s through the same call with HOST (pinned) frame tensors: H2D of
            image+depth+mask every step and a D2H read of the step's scalar result
-  roofline = algorithmic bytes of the integrate kernels (817 B per valid ray)
-           / their CUDA-event time, against the measured HBM peak
+  roofline = the kernel the step spends most of its own-kernel time in: the tcgen05 tap GEMM
+           (csrc/ojdf_conv_tc.cu) of the FusionNet stack -- algorithmic conv FLOPs of FusionNet_v3(sem)
+           (78.15 GFLOP per 240x320 frame) / the CUDA-event time of the engine forward,
+           against the measured dense bf16 tensor peak (sustained figure: the kernel is timed inside
+           a long step); roofline_integrate / roofline_extract = algorithmic bytes (817 B per valid
+           ray / 364 B per ray) / CUDA-event time of those calls, against the measured HBM peak
   cpu_baseline = the CPU port of the same frame (oracle C for extract/integrate + the same
            torch modules on CPU for the two networks) on a bounded sample, rank 0, N=1 only
 
@@ -49,8 +53,8 @@ def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
-    return 6650.0, 'fallback (B200_PROFILING.md)'
+        return float(d['hbm_gbs']), float(d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1400.0))), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1400.0, 'fallback (B200_PROFILING.md)'
 
 
 class ClockSampler:
@@ -265,7 +269,7 @@ def run_own(args):
 
     n_rays = H * W
     nv = float(np.mean([int((hb['mask'] & (hb['tof_depth'] != 0)).sum()) for hb in host_frames]))
-    peak, peak_src = peaks()
+    peak, tpeak, peak_src = peaks()
     int_bytes, ext_bytes = 817.0 * nv, 364.0 * n_rays
     roof_int = {'kernel': 'ojdf_integrate (count + offsets + scatter + rank + finalize kernels)', 'bound': 'hbm',
                 'achieved': int_bytes / (int_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
@@ -275,17 +279,26 @@ def run_own(args):
                 'achieved': ext_bytes / (ext_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
                 'frac': ext_bytes / (ext_ms * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': ext_bytes, 'ms_per_launch': float(ext_ms)}
+    fn_flop = 78.15e9 * (H * W) / 76800.0            # FusionNet_v3 (semantic head on), convolutions only, 2*MAC
+    fn_ms = stages['fusionnet']
+    roof_conv = {'kernel': 'tc::conv_tc_kernel (tcgen05 kind::tf32 tap GEMM, 3xTF32 split precision) over the FusionNet_v3 stack: '
+                           '42 launches per frame + 16 small pooling / bias launches inside the same bracket',
+                 'bound': 'tensor', 'achieved': fn_flop / (fn_ms * 1e-3) / 1e12, 'peak': tpeak, 'unit': 'TFLOP/s',
+                 'frac': fn_flop / (fn_ms * 1e-3) / 1e12 / tpeak, 'traffic': None,
+                 'peak_source': peak_src + ', dense bf16 sustained; the kernel issues 3 tf32 MMAs per algorithmic MAC '
+                                           '(tf32 dense peak is half of bf16), so 1/6 of this peak is its arithmetic ceiling',
+                 'algorithmic_flop_per_frame': fn_flop, 'ms_per_frame': float(fn_ms)} if fn_ms else None
     line = {
         'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64 ray geometry / f32 accumulation / f16+u8 volumes; FusionNet f32 (own fused kernels); AdapNet++ f32 (library convs, TF32 off)',
+        'dtype': 'f64 ray geometry / f32 accumulation / f16+u8 volumes; FusionNet + AdapNet++ 15x20 tail: fp32 via 3xTF32 tcgen05 (own kernels, ~1e-6 of fp32); rest of AdapNet++ f32 library convs (TF32 off)',
         'data': 'synthetic (analytic SDF room, seeded; random-init networks seed 1911)',
         'config': {'workload': WORKLOAD, 'frame': [H, W], 'grid': GRID, 'scenes_per_gpu': SCENES_PER_RANK,
                    'sharding': 'scenes one-per-rank, no collective',
                    'l2': 'inputs larger than L2: %d scenes x 117 MB of volumes rotated every frame + >1 GB of network activations per frame' % SCENES_PER_RANK},
         'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes(host_frames[0]), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'clocks': clocks,
-        'roofline': roof_int, 'roofline_extract': roof_ext,
+        'roofline': roof_conv, 'roofline_integrate': roof_int, 'roofline_extract': roof_ext,
         'stage_ms': stages,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -147,33 +147,31 @@ typedef struct ojdf_conv_problem {
 int ojdf_conv_nhwc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
                            int taps, int act, float slope, float out_mul, float *scratch_dev, size_t scratch_bytes,
                            void *stream);
-/* ---- a10/a17 on the tensor cores: the same tap GEMM as ojdf_conv_nhwc_batched, computed by
- * tcgen05.mma (kind::tf32, TMEM accumulators) with TMA-staged operands and a 3xTF32 split-precision
- * product (x = hi + lo, hi*hi + lo*hi + hi*lo), i.e. fp32-grade results (~1e-6 relative).  Replaces
- * the reference's per-layer cuDNN convolution + BatchNorm + activation launches of
- * modules/model.py:4-283 and modules/adapnet.py:12-415.
- * Weights must be packed with ojdf_conv_tc_pack_weights (host-side; ready-made swizzled shared-memory
- * images [group][tap][kchunk of 32][hi|lo][npad][32]); `weights_dev` of each problem points at the
- * packed copy.  in_dev must be 16-byte aligned with in_stride % 4 == 0; channels >= cin of the input
- * rows are never read (TMA bounds), so a dense-block buffer can be consumed while it grows.
- * flags: bit 0 = do not rewrite the hi tile in shared memory (rely on the hardware ignoring the low
- * 13 mantissa bits of a tf32 operand). */
-int ojdf_conv_tc_layout(int cout, int *npad, int *groups);
-size_t ojdf_conv_tc_weight_floats(int cin, int cout, int taps);
+/* ---- a10/a17 on the tensor cores (csrc/ojdf_conv_tc.cu): the same tap GEMM as ojdf_conv_nhwc_batched,
+ * computed by tcgen05.mma (kind::tf32, fp32 TMEM accumulators) with a 3xTF32 split-precision product
+ * (x = hi + lo; hi*hi + lo*hi + hi*lo), i.e. fp32-grade results (~1e-6 relative).  Replaces the
+ * reference's per-layer cuDNN convolution + BatchNorm + activation launches of modules/model.py:4-283 and
+ * modules/adapnet.py:12-415.  Persistent CTAs (one per SM); one TMA halo box per 32-channel K chunk serves
+ * all 9 taps; the activation operand is split into hi/lo in registers and kept in tensor memory; weight
+ * stages are shared by up to 4 128-pixel M-tiles; double-buffered accumulators; TMA-store epilogue.
+ *   - weights must be packed by ojdf_conv_tc_pack_weights (host side) with the same npad_req as the launch;
+ *     `weights_dev` of each problem points at the device copy of the packed image;
+ *   - in_dev 16-byte aligned, in_stride % 4 == 0; input channels >= cin are never read (TMA bounds), so a
+ *     dense-block buffer can be consumed while it grows;
+ *   - npad_req: 0 = default channel grouping (<= 128 output channels per CTA), or 16..128 (multiple of 16) to
+ *     force narrower groups (more CTAs on small feature maps);
+ *   - flags: 1 = the caller owns the pad channels [coff+cout, coff+round_up(cout,4)) of the output rows (they
+ *     receive zeros; lets a width that is not a multiple of 4 use the TMA-store epilogue, which also needs
+ *     out_coffset % 4 == 0, out_stride % 4 == 0 and a 16-byte aligned out_dev -- otherwise a coalesced plain
+ *     store path is taken); experiments: 2 = one M-tile per group, 4 = never use halo boxes, 8 = per-thread
+ *     stores, 16..2048 and bits 12-15 = timing probes (see the source). */
+int ojdf_conv_tc_layout(int cout, int npad_req, int *npad, int *groups);
+size_t ojdf_conv_tc_weight_floats(int cin, int cout, int taps, int npad_req);
 /* w_host: (cout, cin, taps) fp32 as in nn.Conv2d.weight (tap = ky*3 + kx); packed_host:
  * ojdf_conv_tc_weight_floats() floats. */
-int ojdf_conv_tc_pack_weights(const float *w_host, int cin, int cout, int taps, float *packed_host);
+int ojdf_conv_tc_pack_weights(const float *w_host, int cin, int cout, int taps, int npad_req, float *packed_host);
 int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
-                         int taps, int act, float slope, float out_mul, int flags, void *stream);
-/* Second generation of the same operation (csrc/ojdf_conv_tc2.cu): persistent CTAs, one TMA halo box per
- * K chunk serving all 9 taps, A operand split into hi/lo in registers and kept in tensor memory, weight
- * stages shared by up to 4 M-tiles, double-buffered TMEM accumulators, TMA-store epilogue.  Same
- * arguments and packed weights as ojdf_conv_tc_batched.  flags: 1 = the caller owns the pad channels
- * [coff+cout, coff+round_up(cout,4)) of the output rows (they receive zeros; lets a width that is not a
- * multiple of 4 use the TMA-store epilogue); experiments: 2 = one M-tile per group, 4 = never use halo boxes,
- * 8 = plain stores instead of TMA stores, 16..512 / bits 12-15 = timing probes (see the source). */
-int ojdf_conv_tc2_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
-                          int taps, int act, float slope, float out_mul, int flags, void *stream);
+                         int taps, int act, float slope, float out_mul, int npad_req, int flags, void *stream);
 /* nn.AvgPool2d(3, stride 1, padding 1) of VortexPooling (modules/model.py:114-116), C % 4 == 0. */
 int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int W, int C, float *out_dev, int out_stride,
                        void *stream);

@@ -254,8 +254,35 @@ avgpool3_kernel(const float *__restrict__ in, int in_stride, int H, int W, int C
     reinterpret_cast<float4 *>(out + (size_t)p * out_stride)[c4] = make_float4(s.x / 9.0f, s.y / 9.0f, s.z / 9.0f, s.w / 9.0f);
 }
 
-// Per-channel sums over all pixels (global average pool numerator): partial sums per block row into
-// `partial` [gridDim.x][C]; the tiny second stage runs inside gap_bias_kernel.
+// Per-channel sums over all pixels (global average pool numerator): block b sums its contiguous slice of
+// pixels with float4 loads (thread = one float4 column of one of `lanes` interleaved pixels), folds the
+// pixel lanes through shared memory in a fixed order and writes partial[b][C]; the tiny second stage runs
+// inside gap_bias_kernel.  C % 4 == 0, C <= 1024 (wider inputs take the scalar kernel below).
+__global__ void __launch_bounds__(256)
+channel_sum4_kernel(const float *__restrict__ in, int in_stride, int npix, int C, float *__restrict__ partial)
+{
+    __shared__ float4 s_acc[256];
+    const int c4n = C >> 2, lanes = 256 / c4n;
+    const int c4 = threadIdx.x % c4n, lane = threadIdx.x / c4n;
+    const int per = (npix + gridDim.x - 1) / gridDim.x;
+    const int p0 = blockIdx.x * per, p1 = min(p0 + per, npix);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < lanes)
+        for (int p = p0 + lane; p < p1; p += lanes) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(in + (size_t)p * in_stride) + c4);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+    s_acc[threadIdx.x] = a;
+    __syncthreads();
+    if (lane == 0) {
+        for (int l = 1; l < lanes; ++l) {
+            const float4 v = s_acc[l * c4n + c4];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        reinterpret_cast<float4 *>(partial + (size_t)blockIdx.x * C)[c4] = a;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 channel_sum_kernel(const float *__restrict__ in, int in_stride, int npix, int C, float *__restrict__ partial)
 {
@@ -271,6 +298,8 @@ channel_sum_kernel(const float *__restrict__ in, int in_stride, int npix, int C,
 // mean -> 1x1 conv -> ReLU -> upsample.  Either way the branch is a per-channel constant
 // v[c] = act(g_scale[c] * (wg[c,:] . mean) + g_shift[c]) and the following 1x1 conv sees it as
 // shift_out[co] = f_shift[co] + f_scale[co] * sum_c wf1[co,c] * v[c].   C <= 2048, Cg, Cout <= 256.
+// One block: the partial sums are folded with 4 independent accumulators per channel, the two small
+// matrix-vector products run one output per warp with lanes across the (contiguous) input index.
 __global__ void __launch_bounds__(256)
 gap_bias_kernel(const float *__restrict__ partial, int nblocks, int npix, int C,
                 const float *__restrict__ wg /* [Cg][C] */, const float *__restrict__ g_scale, const float *__restrict__ g_shift, int Cg,
@@ -279,24 +308,37 @@ gap_bias_kernel(const float *__restrict__ partial, int nblocks, int npix, int C,
 {
     __shared__ float s_mean[2048];
     __shared__ float s_v[256];
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int c = t; c < C; c += blockDim.x) {
-        float s = 0.0f;
-        for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * C + c];
-        s_mean[c] = s / (float)npix;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int b = 0;
+        for (; b + 3 < nblocks; b += 4) {
+            s0 += partial[(size_t)b * C + c];
+            s1 += partial[(size_t)(b + 1) * C + c];
+            s2 += partial[(size_t)(b + 2) * C + c];
+            s3 += partial[(size_t)(b + 3) * C + c];
+        }
+        for (; b < nblocks; ++b) s0 += partial[(size_t)b * C + c];
+        s_mean[c] = ((s0 + s1) + (s2 + s3)) / (float)npix;
     }
     __syncthreads();
-    if (t < Cg) {
+    for (int o = warp; o < Cg; o += 8) {
         float a = 0.0f;
-        for (int c = 0; c < C; ++c) a = fmaf(wg[(size_t)t * C + c], s_mean[c], a);
-        a = fmaf(a, g_scale[t], g_shift[t]);
-        s_v[t] = v_relu ? fmaxf(a, 0.0f) : a;
+        for (int c = lane; c < C; c += 32) a = fmaf(__ldg(wg + (size_t)o * C + c), s_mean[c], a);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+        if (lane == 0) {
+            a = fmaf(a, g_scale[o], g_shift[o]);
+            s_v[o] = v_relu ? fmaxf(a, 0.0f) : a;
+        }
     }
     __syncthreads();
-    if (t < Cout) {
+    for (int o = warp; o < Cout; o += 8) {
         float a = 0.0f;
-        for (int c = 0; c < Cg; ++c) a = fmaf(wf1[(size_t)t * Cg + c], s_v[c], a);
-        shift_out[t] = fmaf(a, f_scale[t], f_shift[t]);
+        for (int c = lane; c < Cg; c += 32) a = fmaf(__ldg(wf1 + (size_t)o * Cg + c), s_v[c], a);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+        if (lane == 0) shift_out[o] = fmaf(a, f_scale[o], f_shift[o]);
     }
 }
 
@@ -473,7 +515,10 @@ extern "C" int ojdf_gap_bias(const float *in_dev, int in_stride, int npix, int C
         return OJDF_ERR_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
     const int pb = partial_blocks < npix ? partial_blocks : npix;
-    channel_sum_kernel<<<dim3(pb, (C + 255) / 256), 256, 0, s>>>(in_dev, in_stride, npix, C, partial_dev);
+    if (!(C & 3) && C <= 1024 && !(in_stride & 3) && !((uintptr_t)in_dev & 15))
+        channel_sum4_kernel<<<pb, 256, 0, s>>>(in_dev, in_stride, npix, C, partial_dev);
+    else
+        channel_sum_kernel<<<dim3(pb, (C + 255) / 256), 256, 0, s>>>(in_dev, in_stride, npix, C, partial_dev);
     gap_bias_kernel<<<1, 256, 0, s>>>(partial_dev, pb, npix, C, wg_dev, g_scale_dev, g_shift_dev, Cg, v_relu, wf1_dev,
                                      f_scale_dev, f_shift_dev, Cout, shift_out_dev);
     return launched(2);

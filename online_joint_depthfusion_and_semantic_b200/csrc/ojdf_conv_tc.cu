@@ -1,70 +1,72 @@
-// Tensor-core version of the tap GEMM of ojdf_conv.cu: tcgen05.mma (kind::tf32) with TMEM accumulators,
-// TMA-staged operands and a split-precision (3xTF32) product so that the result stays within ~1e-6 of
-// the fp32 convolution of the reference (modules/model.py:4-283, modules/adapnet.py:12-415).
+// Persistent tensor-core tap GEMM of FusionNet / AdapNet++ (modules/model.py:4-283, modules/adapnet.py:12-415):
 //
 //   out[p, coff+co] = out_mul * act(scale[co] * sum_tap sum_ci in[p + tap*dil, ci] * W[tap,ci,co] + shift[co] (+ residual))
 //
-// GEMM view, per CTA: M = 128 output pixels (a BH x BW rectangle of the image, BH*BW = 128), N = NPAD
-// output channels (cout padded to 16, <= 128 per CTA), K = taps x cin in chunks of 32 channels.
-//   * A (pixels x channels, K-major): the activation tensor is pixel-major (H, W, C) fp32; one TMA box
-//     (32 channels, BW, BH) at the tap-shifted coordinate lands in shared memory as 128 rows of 128 bytes
-//     in the SWIZZLE_128B pattern -- exactly the canonical K-major UMMA operand.  The convolution's zero
-//     padding, the channel tail (cin not a multiple of 32) and partial tiles at the image border are all
-//     TMA out-of-bounds zero fill: no masks, no im2col buffer.
-//   * B (channels_out x channels_in, K-major): weights are packed on the host once
-//     (ojdf_conv_tc_pack_weights) as ready-made swizzled shared-memory images [group][tap][kchunk][hi|lo]
-//     [NPAD rows][32], fetched with one cp.async.bulk per chunk.
-//   * 3xTF32: kind::tf32 reads fp32 containers and uses the top 19 bits.  x = hi + lo with hi = x with
-//     the low 13 mantissa bits cleared and lo = x - hi (exact); D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo
-//     drops only lo*lo (2^-22 relative).  The weight split is done by the packer; the activation split is
-//     done in shared memory by the four epilogue warps while they wait (a second 16 KB tile per stage).
-//   * Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
-//     warps 2..5 = hi/lo splitter during the main loop, then epilogue (tcgen05.ld -> scale/shift/residual/
-//     activation -> pixel-major stores).  mbarrier rings: full (TMA landed) -> split (lo tile written) ->
-//     MMA -> empty (tcgen05.commit) ; acc (all MMAs retired) -> epilogue.
-//   * One tile per CTA, 1-2 CTAs per SM (each owns its TMEM columns), up to 8 equally shaped problems
-//     per launch along blockIdx.z (the two FusionNet heads, the four VortexPooling branches).
+// on tcgen05.mma kind::tf32 with the 3xTF32 split (x = hi + lo; hi*hi + lo*hi + hi*lo) and fp32 TMEM
+// accumulators (results within ~1e-6 of an fp32 convolution; kind::tf32 uses the top 19 bits of an fp32
+// container, hi = x with the low 13 mantissa bits cleared, lo = x - hi exactly, only lo*lo is dropped).
+// Design, each point measured on B200 against a first version that issued one 16 KB TMA box per tap and
+// one tile per CTA (bound by L2->SM traffic and per-CTA prologue/epilogue):
+//   * one CTA per SM, persistent over a contiguous range of 128-pixel M-tiles (8 rows x 16 columns each,
+//     column-major over the image so that up to MT vertically adjacent M-tiles form one work group);
+//   * the activation HALO of a group ((8*MT + 2d) x (16 + 2d) pixels x 32 channels) is fetched ONCE per
+//     K chunk by a single TMA box (zero fill = convolution padding / channel tail / image border) and
+//     serves all 9 taps; huge dilations (halo would not fit) fall back to one box per tap;
+//   * the A operand lives in TENSOR MEMORY: eight "splitter" warps read the tap-shifted pixel rows out
+//     of the swizzled halo tile (conflict-free LDS.128), split them into hi/lo in registers and
+//     tcgen05.st both halves into a 4-deep TMEM ring; tcgen05.mma reads A from TMEM and only the small
+//     weight tiles (B, K-major SWIZZLE_128B images packed by the host) from shared memory -- shared
+//     memory carries each activation byte once per tap instead of five times;
+//   * one weight stage (tap, K chunk) is reused by all MT M-tiles of the group;
+//   * accumulators are double buffered in TMEM (when 2*MT*NPAD <= 256 columns) so the epilogue of one
+//     group (tcgen05.ld -> scale/shift/residual/activation -> swizzled staging tile -> TMA store, clipped
+//     by the tensor map to the image and to channels < coff+cout) overlaps the main loop of the next.
+// Warp roles (608 threads): 0 = TMA producer, 1 and 18 = MMA issuers (even / odd M-tiles of a group; warp 1
+// also owns the TMEM allocation), 2..9 = splitters (two sets of four, alternating A stages), 10..17 =
+// epilogue (two warps per TMEM lane quarter, alternating 16-column chunks).
 #include <cuda.h>
 
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
-#include <vector>
 
 #include "ojdf_internal.h"
 
 namespace ojdf {
 namespace tc {
 
-constexpr int kBK = 32;                 // fp32 channels per K chunk: 128 bytes = one swizzle row
-constexpr int kM = 128;                 // pixels per CTA tile (UMMA M)
-constexpr int kATileBytes = kM * 128;   // 16 KB
-constexpr int kThreads = 192;
+constexpr int kBK = 32;                  // fp32 channels per K chunk (128 bytes)
+constexpr int kBW = 16, kBH = 8;         // M-tile = 8 rows x 16 columns = 128 pixels
+constexpr int kThreads = 608;              // 19 warps, see the role list above
+constexpr int kEpi0 = 10, kEpiThreads = 256;   // epilogue warps 10..17
+constexpr int kMma2 = 18;                      // second MMA issuer
 constexpr int kMaxBatch = 8;
-constexpr int kMaxStages = 6;
-constexpr long long kSpinLimit = 4000000000LL;   // ~2 s of SM clocks: a wedged pipeline traps instead of hanging
+constexpr int kAS = 6;                   // most A stages in TMEM (64 columns each: hi 32 | lo 32); the ring of an
+                                         // issuer/splitter pair has prm.a_slots of them, starting at column prm.acol0
+constexpr int kMaxSrc = 4, kMaxB = 8;
+constexpr int kSlabBytes = 128 * 128;    // staging slab: 128 pixels x 32 channels
 
 enum Act { kNone = 0, kRelu = 1, kLeaky = 2, kTanh = 3, kSigmoid = 4 };
 
 struct Problem {
-    const float *weights;       // packed images of this problem
-    const float *scale, *shift;
+    const float *weights, *scale, *shift;
     float *out;
     const float *residual;
     int out_stride, out_coff, dil, res_stride;
 };
 
 struct Params {
-    CUtensorMap tmap[kMaxBatch];
+    CUtensorMap in_map[kMaxBatch];
+    CUtensorMap out_map[kMaxBatch];
     Problem p[kMaxBatch];
-    int H, W, cin, cout, taps, act, npad, nkc, stages, bw, bh, tiles_x, exact_hi;
+    int H, W, cin, cout, taps, act, npad, groups, nkc, tiles_x, tiles_y, nprob;
+    int mt, nacc, hd, src_stages, b_stages, src_bytes, box_bytes, bwid, store_mode, dbg, sub_rows, nsub, a_slots, acol0;
     float slope, out_mul;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -77,25 +79,69 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+// Wait for a phase of an mbarrier.  try_wait with a suspend-time hint parks the warp in hardware (no issue
+// slots burnt by the many waiting roles); a pipeline that is wedged for ~2 s traps instead of hanging.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint = 0x989680u)
 {
     uint32_t done = 0;
-    const long long t0 = clock64();
-    while (true) {
+    for (int spins = 0;; ++spins) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(hint)
+            : "memory");
+        if (done) break;
+        if (spins > 20000000) {
+            printf("ojdf conv_tc: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x,
+                   bar, parity);
+            __trap();
+        }
+    }
+}
+// Busy poll with the non-blocking test_wait: for the hot A-ring hand-offs, where parking the warp costs more
+// than the few issue slots the poll takes.
+__device__ __forceinline__ void mbar_poll(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (int spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        if (clock64() - t0 > kSpinLimit) {
-            printf("ojdf conv_tc: mbarrier wait timed out (block %d,%d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x,
-                   blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+        if (spins > 100000000) {
+            printf("ojdf conv_tc: mbarrier poll timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x,
+                   bar, parity);
             __trap();
         }
     }
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// Optional role profile (flag 128, block 0 only): cycles each role spent waiting per barrier class.
+__device__ long long g_prof[32];
+__device__ __forceinline__ void mbar_wait_p(uint32_t bar, uint32_t parity, int cls, bool on, uint32_t hint = 0x989680u)
+{
+    if (!on) {
+        if (hint) mbar_wait(bar, parity, hint); else mbar_poll(bar, parity);
+        return;
+    }
+    const long long t0 = clock64();
+    if (hint) mbar_wait(bar, parity, hint); else mbar_poll(bar, parity);
+    if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&g_prof[cls], (unsigned long long)(clock64() - t0));
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
 {
@@ -103,6 +149,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1), "r"(c2)
+                 : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
@@ -113,31 +165,30 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major, kind::tf32, issued by one thread.
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+// D[tmem] (+)= A[tmem] * B[smem]^T ; A: 128 lanes x 8 columns of tf32, B: K-major SWIZZLE_128B descriptor.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr)
 {
     uint64_t d = 0;
-    d |= (uint64_t)((addr & 0x3FFFF) >> 4);           // start address
-    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
     return d;
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
@@ -150,6 +201,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float activate(float v, int act, float slope)
 {
@@ -160,155 +223,357 @@ __device__ __forceinline__ float activate(float v, int act, float slope)
     return v;
 }
 
-// dynamic smem: [stages] x { A_hi 16 KB | A_lo 16 KB | B_hi npad*128 | B_lo npad*128 }, 1024-byte aligned,
-// then the barriers.
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ Params prm)
+// 16 accumulator columns -> scale/shift (+ residual) -> activation.  `ncols` = real channels left in this chunk.
+template <int ACT>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[16], float (&o)[16], const float2 *ss, const float *res, int ncols,
+                                          float slope, float out_mul)
+{
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const float2 p = ss[c];
+        float r = fmaf(__uint_as_float(v[c]), p.x, p.y);
+        if (res && c < ncols) r += res[c];
+        if (ACT == kRelu) r = fmaxf(r, 0.0f);
+        if (ACT == kLeaky) r = r > 0.0f ? r : r * slope;
+        if (ACT == kTanh) r = tanhf(r);
+        if (ACT == kSigmoid) r = 1.0f / (1.0f + expf(-r));
+        o[c] = r * out_mul;
+    }
+}
+
+// One work group: up to MT vertically adjacent M-tiles of one (problem, channel group).
+struct Group { int z, g, col, row, n; };
+__device__ __forceinline__ Group decode(const Params &prm, int s, int end)
+{
+    const int tiles = prm.tiles_x * prm.tiles_y;
+    Group gr;
+    const int t = s % tiles, zg = s / tiles;
+    gr.g = zg % prm.groups;
+    gr.z = zg / prm.groups;
+    gr.col = t / prm.tiles_y;
+    gr.row = t - gr.col * prm.tiles_y;
+    int n = prm.mt;
+    if (n > end - s) n = end - s;
+    if (n > prm.tiles_y - gr.row) n = prm.tiles_y - gr.row;
+    gr.n = n;
+    return gr;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ Params prm)
 {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_bars[3 * kMaxStages + 1];
+    __shared__ __align__(8) uint64_t s_bars[2 * kMaxSrc + 2 * kMaxB + 2 * kAS + 4];
     __shared__ uint32_t s_tmem;
+    __shared__ float2 s_ss[128];                                 // (scale, shift) of the epilogue's current channel group
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // warp-uniform role index
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - raw);
-    const int S = prm.stages, npad = prm.npad;
-    const uint32_t b_bytes = (uint32_t)npad * 128u;            // one of B_hi / B_lo
-    const uint32_t stage_bytes = 2u * kATileBytes + 2u * b_bytes;
+    const int npad = prm.npad, HS = prm.src_stages, BS = prm.b_stages, MT = prm.mt, NACC = prm.nacc;
+    const uint32_t b_bytes = (uint32_t)npad * 128u;             // one of B_hi / B_lo
+    const uint32_t src0 = base;
+    const uint32_t bst0 = src0 + (uint32_t)HS * prm.src_bytes;
+    const uint32_t stg0 = bst0 + (uint32_t)BS * 2u * b_bytes;
+    uint8_t *stg_ptr = smem + (size_t)HS * prm.src_bytes + (size_t)BS * 2u * b_bytes;
     const uint32_t bar0 = smem_u32(s_bars);
-    auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto split_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + s); };
-    const uint32_t acc_bar = bar0 + 8u * (3 * kMaxStages);
+    auto src_full = [&](int s) { return bar0 + 8u * s; };
+    auto src_empty = [&](int s) { return bar0 + 8u * (kMaxSrc + s); };
+    auto b_full = [&](int s) { return bar0 + 8u * (2 * kMaxSrc + s); };
+    auto b_empty = [&](int s) { return bar0 + 8u * (2 * kMaxSrc + kMaxB + s); };
+    auto a_full = [&](int s) { return bar0 + 8u * (2 * kMaxSrc + 2 * kMaxB + s); };
+    auto a_empty = [&](int s) { return bar0 + 8u * (2 * kMaxSrc + 2 * kMaxB + kAS + s); };
+    auto acc_full = [&](int s) { return bar0 + 8u * (2 * kMaxSrc + 2 * kMaxB + 2 * kAS + s); };
+    auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kMaxSrc + 2 * kMaxB + 2 * kAS + 2 + s); };
 
-    const Problem &pr = prm.p[blockIdx.z];
-    const int tile_y = blockIdx.x / prm.tiles_x, tile_x = blockIdx.x - tile_y * prm.tiles_x;
-    const int x0 = tile_x * prm.bw, y0 = tile_y * prm.bh;
-    const int group = blockIdx.y;
-    const int n_iter = prm.taps * prm.nkc;
-
-    uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)npad) tmem_cols <<= 1;
+    const int tiles = prm.tiles_x * prm.tiles_y;
+    const int total = prm.nprob * prm.groups * tiles;
+    const int begin = (int)((long long)total * blockIdx.x / gridDim.x);
+    const int end = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
+    const uint32_t hot_hint = (prm.dbg & 1024) ? 0u : 0x989680u;   // experiment: do not park the A-ring waiters
+    const bool halo_mode = prm.hd > 0 || prm.taps == 1;
+    const int nbox = halo_mode ? 1 : prm.taps;                   // TMA boxes per K chunk
+    const int taps_per_box = halo_mode ? prm.taps : 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(split_bar(s), 128);
-            mbar_init(empty_bar(s), 1);
-        }
-        mbar_init(acc_bar, 1);
+        for (int s = 0; s < kMaxSrc; ++s) { mbar_init(src_full(s), 1); mbar_init(src_empty(s), 256); }
+        for (int s = 0; s < kMaxB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 2); }
+        for (int s = 0; s < kAS; ++s) { mbar_init(a_full(s), 128); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 2); mbar_init(acc_empty(s), kEpiThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols)
-                     : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+    const bool prof = (prm.dbg & 128) && blockIdx.x == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6 || warp == kEpi0);
+    const long long t_role0 = prof ? clock64() : 0;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            const CUtensorMap *map = &prm.tmap[blockIdx.z];
-            const uint8_t *wbase = reinterpret_cast<const uint8_t *>(pr.weights) + (size_t)group * n_iter * 2u * b_bytes;
-            int tap = 0, kc = 0;
-            for (int it = 0; it < n_iter; ++it) {
-                const int s = it % S;
-                if (it >= S) mbar_wait(empty_bar(s), ((it / S) - 1) & 1);
-                const int dy = prm.taps == 1 ? 0 : (tap / 3 - 1) * pr.dil, dx = prm.taps == 1 ? 0 : (tap % 3 - 1) * pr.dil;
-                const uint32_t sa = base + (uint32_t)s * stage_bytes;
-                mbar_expect_tx(full_bar(s), kATileBytes + 2u * b_bytes);
-                tma_load_3d(sa, map, full_bar(s), kc * kBK, x0 + dx, y0 + dy);
-                bulk_load(sa + 2u * kATileBytes, wbase + (size_t)it * 2u * b_bytes, 2u * b_bytes, full_bar(s));
-                if (++kc == prm.nkc) { kc = 0; ++tap; }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            // instruction descriptor: D f32, A/B tf32, both K-major, N = npad, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
-            for (int it = 0; it < n_iter; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (it / S) & 1;
-                mbar_wait(full_bar(s), ph);
-                mbar_wait(split_bar(s), ph);
-                tc_fence_after();
-                const uint32_t sa = base + (uint32_t)s * stage_bytes;
-                const uint64_t a_hi = smem_desc(sa), a_lo = smem_desc(sa + kATileBytes);
-                const uint64_t b_hi = smem_desc(sa + 2u * kATileBytes), b_lo = smem_desc(sa + 2u * kATileBytes + b_bytes);
-#pragma unroll
-                for (int k = 0; k < kBK / 8; ++k) {
-                    const uint64_t ko = (uint64_t)(k * 32 >> 4);       // +32 bytes along K inside the swizzle atom
-                    umma_tf32(tmem, a_lo + ko, b_hi + ko, idesc, (it | k) != 0);
-                    umma_tf32(tmem, a_hi + ko, b_lo + ko, idesc, 1);
-                    umma_tf32(tmem, a_hi + ko, b_hi + ko, idesc, 1);
-                }
-                umma_commit(empty_bar(s));
-            }
-            umma_commit(acc_bar);
-        }
-    } else {
-        // ------------------------------------------------------------ splitter, then epilogue
-        const int t = threadIdx.x - 64;                        // 0..127
-        for (int it = 0; it < n_iter; ++it) {
-            const int s = it % S;
-            mbar_wait(full_bar(s), (it / S) & 1);
-            uint4 *hi = reinterpret_cast<uint4 *>(smem + (size_t)s * stage_bytes);
-            uint4 *lo = reinterpret_cast<uint4 *>(smem + (size_t)s * stage_bytes + kATileBytes);
-#pragma unroll
-            for (int j = 0; j < kATileBytes / 16 / 128; ++j) {
-                const int i = t + 128 * j;
-                const uint4 x = hi[i];
-                uint4 h, l;
-                h.x = x.x & 0xFFFFE000u; h.y = x.y & 0xFFFFE000u; h.z = x.z & 0xFFFFE000u; h.w = x.w & 0xFFFFE000u;
-                l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
-                l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
-                l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
-                l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
-                lo[i] = l;
-                if (prm.exact_hi) hi[i] = h;
-            }
-            fence_proxy_async();
-            mbar_arrive(split_bar(s));
-        }
-        // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 ; lane = accumulator row = pixel of the tile
-        mbar_wait(acc_bar, 0);
-        tc_fence_after();
-        const int q = warp & 3;
-        const int m = q * 32 + lane;
-        const int ty = m / prm.bw, tx = m - ty * prm.bw;
-        const int y = y0 + ty, x = x0 + tx;
-        const bool live = ty < prm.bh && y < prm.H && x < prm.W;
-        const size_t pix = (size_t)y * prm.W + x;
-        const int co_base = group * npad;
-        float *orow = pr.out + pix * pr.out_stride + pr.out_coff + co_base;
-        const float *rrow = pr.residual ? pr.residual + pix * pr.res_stride + co_base : nullptr;
-        for (int n0 = 0; n0 < npad; n0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, v);
-            tmem_ld_wait();
-            if (live) {
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const int co = co_base + n0 + c;
-                    if (co < prm.cout) {
-                        float r = fmaf(__uint_as_float(v[c]), __ldg(pr.scale + co), __ldg(pr.shift + co));
-                        if (rrow) r += rrow[n0 + c];
-                        orow[n0 + c] = activate(r, prm.act, prm.slope) * prm.out_mul;
+        // ------------------------------------------------------------ TMA producer (whole warp walks the loop, one
+        // elected lane issues: keeps addresses and barrier numbers in uniform registers)
+        int src_i = 0, b_i = 0;
+        for (int s = begin; s < end;) {
+            const Group gr = decode(prm, s, end);
+            const Problem &pr = prm.p[gr.z];
+            const CUtensorMap *map = &prm.in_map[gr.z];
+            const int x0 = gr.col * kBW, y0 = gr.row * kBH;
+            const uint8_t *wbase = reinterpret_cast<const uint8_t *>(pr.weights) + (size_t)gr.g * prm.taps * prm.nkc * 2u * b_bytes;
+            for (int kc = 0; kc < prm.nkc; ++kc) {
+                for (int box = 0; box < nbox; ++box) {
+                    const int slot = src_i % HS;
+                    if (src_i >= HS) mbar_wait_p(src_empty(slot), ((src_i / HS) - 1) & 1, 0, prof);
+                    int cx = x0 - prm.hd, cy = y0 - prm.hd;
+                    if (!halo_mode) { cx = x0 + (box % 3 - 1) * pr.dil; cy = y0 + (box / 3 - 1) * pr.dil; }
+                    if (elect_one()) {
+                        mbar_expect_tx(src_full(slot), (uint32_t)prm.box_bytes);
+                        for (int i = 0; i < prm.nsub; ++i)
+                            tma_load_3d(src0 + (uint32_t)slot * prm.src_bytes + (uint32_t)(i * prm.sub_rows * prm.bwid * 128), map,
+                                        src_full(slot), kc * kBK, cx, cy + i * prm.sub_rows);
+                    }
+                    __syncwarp();
+                    ++src_i;
+                    for (int tb = 0; tb < taps_per_box; ++tb) {
+                        const int tap = halo_mode ? tb : box;
+                        const int bs = b_i % BS;
+                        if (b_i >= BS) mbar_wait_p(b_empty(bs), ((b_i / BS) - 1) & 1, 1, prof);
+                        if (elect_one()) {
+                            mbar_expect_tx(b_full(bs), 2u * b_bytes);
+                            bulk_load(bst0 + (uint32_t)bs * 2u * b_bytes, wbase + (size_t)(tap * prm.nkc + kc) * 2u * b_bytes,
+                                      2u * b_bytes, b_full(bs));
+                        }
+                        __syncwarp();
+                        ++b_i;
                     }
                 }
             }
+            s += gr.n;
         }
+    } else if (warp == 1 || warp == kMma2) {
+        // ------------------------------------------------------------ MMA issuers (uniform loop, elected lane issues);
+        // warp 1 owns the even M-tiles of every group, warp 18 the odd ones: each accumulator has one issuer
+        const int par = warp == 1 ? 0 : 1;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        int cnt = 0, b_i = 0, gc = 0;                           // cnt: A stages consumed by this issuer
+        for (int s = begin; s < end; ++gc) {
+            const Group gr = decode(prm, s, end);
+            const int buf = gc % NACC;
+            if (gc >= NACC) mbar_wait_p(acc_empty(buf), ((gc / NACC) - 1) & 1, 3, prof);
+            tc_fence_after();
+            for (int kc = 0; kc < prm.nkc; ++kc) {
+                for (int tap = 0; tap < prm.taps; ++tap) {
+                    const int bs = b_i % BS;
+                    mbar_wait_p(b_full(bs), (b_i / BS) & 1, 4, prof);
+                    const uint32_t sb = bst0 + (uint32_t)bs * 2u * b_bytes;
+                    const uint64_t b_hi = smem_desc(sb), b_lo = smem_desc(sb + b_bytes);
+                    for (int mt = par; mt < gr.n; mt += 2, ++cnt) {
+                        // issuer `par` and splitter set `par` form an in-order pipeline over A slots 2*par, 2*par+1
+                        const int as = par * prm.a_slots + cnt % prm.a_slots;
+                        mbar_wait_p(a_full(as), (cnt / prm.a_slots) & 1, 5, prof, hot_hint);
+                        if (!(prm.dbg & 512)) tc_fence_after();
+                        const uint32_t acc = tmem + (uint32_t)((buf * MT + mt) * npad);
+                        const uint32_t a_hi = tmem + (uint32_t)(prm.acol0 + as * 64), a_lo = a_hi + 32;
+                        const uint32_t first = (uint32_t)(kc | tap);
+                        if (elect_one()) {
+                            if (!(prm.dbg & 16)) {
+                                if (prm.dbg & 64) {                          // timing experiment: 1xTF32
+#pragma unroll
+                                    for (int k = 0; k < kBK / 8; ++k)
+                                        umma_tf32_ts(acc, a_hi + k * 8, b_hi + (uint64_t)(k * 2), idesc, first | (uint32_t)k);
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < kBK / 8; ++k) {
+                                        const uint64_t ko = (uint64_t)(k * 2);   // +32 bytes along K inside the swizzle atom
+                                        umma_tf32_ts(acc, a_lo + k * 8, b_hi + ko, idesc, first | (uint32_t)k);
+                                        umma_tf32_ts(acc, a_hi + k * 8, b_lo + ko, idesc, 1);
+                                        umma_tf32_ts(acc, a_hi + k * 8, b_hi + ko, idesc, 1);
+                                    }
+                                }
+                            }
+                            if (prm.dbg & 256) mbar_arrive(a_empty(as)); else umma_commit(a_empty(as));
+                        }
+                        __syncwarp();
+                    }
+                    if (elect_one()) umma_commit(b_empty(bs));
+                    __syncwarp();
+                    ++b_i;
+                }
+            }
+            if (elect_one()) umma_commit(acc_full(buf));
+            __syncwarp();
+            s += gr.n;
+        }
+    } else if (warp < kEpi0) {
+        // ------------------------------------------------------------ splitters: halo tile -> hi/lo -> TMEM A ring
+        const int set = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int m = q * 32 + lane, ty = m / kBW, tx = m % kBW;
+        int cnt = 0, src_i = 0;                                 // cnt: A stages produced by this set
+        for (int s = begin; s < end;) {
+            const Group gr = decode(prm, s, end);
+            const int dil = prm.p[gr.z].dil;
+            for (int kc = 0; kc < prm.nkc; ++kc) {
+                for (int box = 0; box < nbox; ++box) {
+                    const int slot = src_i % HS;
+                    mbar_wait_p(src_full(slot), (src_i / HS) & 1, 7 + 3 * set, prof);
+                    const uint8_t *src = smem + (size_t)slot * prm.src_bytes;
+                    for (int tb = 0; tb < taps_per_box; ++tb) {
+                        int oy = 0, ox = 0;
+                        if (halo_mode && prm.taps == 9) { oy = prm.hd + (tb / 3 - 1) * dil; ox = prm.hd + (tb % 3 - 1) * dil; }
+                        for (int mt = set; mt < gr.n; mt += 2, ++cnt) {
+                            const int as = set * prm.a_slots + cnt % prm.a_slots, use = cnt / prm.a_slots;
+                            if (prm.dbg & 32) {                                  // timing experiment: no split work
+                                if (use >= 1) mbar_wait(a_empty(as), (use - 1) & 1);
+                                mbar_arrive(a_full(as));
+                                continue;
+                            }
+                            const int r = (mt * kBH + ty + oy) * prm.bwid + tx + ox;
+                            const uint4 *row = reinterpret_cast<const uint4 *>(src + (size_t)r * 128);
+                            uint32_t hi[32], lo[32];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const uint4 x = row[j ^ (r & 7)];
+                                const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const uint32_t h = xs[e] & 0xFFFFE000u;
+                                    hi[4 * j + e] = h;
+                                    lo[4 * j + e] = __float_as_uint(__uint_as_float(xs[e]) - __uint_as_float(h));
+                                }
+                            }
+                            if (use >= 1) mbar_wait_p(a_empty(as), (use - 1) & 1, 8 + 3 * set, prof, hot_hint);
+                            tc_fence_after();
+                            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(prm.acol0 + as * 64);
+                            tmem_st32(ta, hi);
+                            tmem_st32(ta + 32, lo);
+                            tmem_st_wait();
+                            tc_fence_before();
+                            mbar_arrive(a_full(as));
+                        }
+                    }
+                    mbar_arrive(src_empty(slot));
+                    ++src_i;
+                }
+            }
+            s += gr.n;
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: 8 warps; warp pair (q, half) owns TMEM
+        // lanes 32q..32q+31 and the 16-column chunks with index = half (mod 2)
+        const int q = warp & 3, half = (warp - kEpi0) >> 2;
+        const int et = threadIdx.x - kEpi0 * 32;                // 0..255
+        const int m = q * 32 + lane, ty = m / kBW, tx = m % kBW;
+        const int nslab = (npad + 31) / 32;
+        int gc = 0, cur_zg = -1;
+        for (int s = begin; s < end; ++gc) {
+            const Group gr = decode(prm, s, end);
+            const Problem &pr = prm.p[gr.z];
+            const int buf = gc % NACC;
+            const int co_base = gr.g * npad;
+            if (cur_zg != gr.z * prm.groups + gr.g) {            // (scale, shift) of this channel group -> smem
+                named_bar(1, kEpiThreads);
+                if (et < npad) {
+                    const int co = co_base + et;
+                    s_ss[et] = co < prm.cout ? make_float2(__ldg(pr.scale + co), __ldg(pr.shift + co)) : make_float2(0.f, 0.f);
+                }
+                named_bar(1, kEpiThreads);
+                cur_zg = gr.z * prm.groups + gr.g;
+            }
+            mbar_wait_p(acc_full(buf), (gc / NACC) & 1, 13, prof);
+            tc_fence_after();
+            for (int mt = 0; mt < gr.n; ++mt) {
+                const int x = gr.col * kBW + tx, y = (gr.row + mt) * kBH + ty;
+                const bool live = y < prm.H && x < prm.W;
+                const size_t pix = (size_t)y * prm.W + x;
+                const float *rrow = (pr.residual && live) ? pr.residual + pix * pr.res_stride + co_base : nullptr;
+                const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * MT + mt) * npad);
+                if (prm.store_mode == 0 && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (prm.store_mode != 2) named_bar(1, kEpiThreads);      // the previous store pass has drained the staging tile
+                for (int n0 = half * 16; n0 < npad; n0 += 32) {
+                    uint32_t v[16];
+                    tmem_ld16(tacc + (uint32_t)n0, v);
+                    tmem_ld_wait();
+                    float o[16];
+                    switch (prm.act) {                           // uniform branch; the element loops are branch-free
+                        case kRelu: epi_chunk<kRelu>(v, o, s_ss + n0, rrow ? rrow + n0 : nullptr, prm.cout - co_base - n0, prm.slope, prm.out_mul); break;
+                        case kLeaky: epi_chunk<kLeaky>(v, o, s_ss + n0, rrow ? rrow + n0 : nullptr, prm.cout - co_base - n0, prm.slope, prm.out_mul); break;
+                        case kTanh: epi_chunk<kTanh>(v, o, s_ss + n0, rrow ? rrow + n0 : nullptr, prm.cout - co_base - n0, prm.slope, prm.out_mul); break;
+                        case kSigmoid: epi_chunk<kSigmoid>(v, o, s_ss + n0, rrow ? rrow + n0 : nullptr, prm.cout - co_base - n0, prm.slope, prm.out_mul); break;
+                        default: epi_chunk<kNone>(v, o, s_ss + n0, rrow ? rrow + n0 : nullptr, prm.cout - co_base - n0, prm.slope, prm.out_mul); break;
+                    }
+                    if (prm.store_mode == 2) {
+                        if (live) {
+                            float *orow = pr.out + pix * pr.out_stride + pr.out_coff + co_base;
+#pragma unroll
+                            for (int c = 0; c < 16; ++c)
+                                if (co_base + n0 + c < prm.cout) orow[n0 + c] = o[c];
+                        }
+                    } else {
+                        // staging slab (n0/32): 128 rows of 128 bytes, SWIZZLE_128B like the tensor map expects
+                        uint8_t *slab = stg_ptr + (size_t)(n0 >> 5) * kSlabBytes + (size_t)m * 128;
+                        const int j0 = (n0 & 16) >> 2;           // first 16-byte chunk of this half row
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<float4 *>(slab + (((j0 + j) ^ (m & 7)) << 4)) =
+                                make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    }
+                }
+                if (prm.store_mode == 0) {
+                    fence_proxy_async();
+                    named_bar(1, kEpiThreads);
+                    if (et == 0) {
+                        for (int sl = 0; sl < nslab; ++sl)
+                            tma_store_3d(&prm.out_map[gr.z], stg0 + (uint32_t)sl * kSlabBytes, pr.out_coff + co_base + sl * 32,
+                                         gr.col * kBW, (gr.row + mt) * kBH);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                } else if (prm.store_mode == 1) {
+                    // row-contiguous stores out of the staging tile: consecutive lanes write consecutive channels
+                    // of one pixel (unaligned channel offsets / widths the TMA store cannot express)
+                    named_bar(1, kEpiThreads);
+                    int nco = prm.cout - co_base;
+                    if (nco > npad) nco = npad;
+                    const int rbeg = q * 32 + half * 16, rend = rbeg + 16;
+                    if (nco <= 32) {
+                        const int lanes_per_row = nco <= 16 ? 16 : 32, rpp = 32 / lanes_per_row;
+                        const int c = lane % lanes_per_row, rsub = lane / lanes_per_row;
+                        for (int r0 = rbeg; r0 < rend; r0 += rpp) {
+                            const int rr = r0 + rsub;
+                            const int px = gr.col * kBW + rr % kBW, py = (gr.row + mt) * kBH + rr / kBW;
+                            if (c < nco && py < prm.H && px < prm.W) {
+                                const float v = *reinterpret_cast<const float *>(stg_ptr + (size_t)rr * 128 + (((c >> 2) ^ (rr & 7)) << 4) + ((c & 3) << 2));
+                                pr.out[((size_t)py * prm.W + px) * pr.out_stride + pr.out_coff + co_base + c] = v;
+                            }
+                        }
+                    } else {
+                        for (int rr = rbeg; rr < rend; ++rr) {
+                            const int px = gr.col * kBW + rr % kBW, py = (gr.row + mt) * kBH + rr / kBW;
+                            if (py >= prm.H || px >= prm.W) continue;
+                            float *orow = pr.out + ((size_t)py * prm.W + px) * pr.out_stride + pr.out_coff + co_base;
+                            for (int c = lane; c < nco; c += 32)
+                                orow[c] = *reinterpret_cast<const float *>(stg_ptr + (size_t)(c >> 5) * kSlabBytes + (size_t)rr * 128 +
+                                                                           ((((c & 31) >> 2) ^ (rr & 7)) << 4) + ((c & 3) << 2));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acc_empty(buf));
+            s += gr.n;
+        }
+        if (prm.store_mode == 0 && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    if (prof && lane == 0) {
+        const int slot = warp == 0 ? 2 : warp == 1 ? 6 : warp == 2 ? 9 : warp == 6 ? 12 : 14;     // warp kEpi0 -> 14
+        atomicAdd((unsigned long long *)&g_prof[slot], (unsigned long long)(clock64() - t_role0));
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
-    }
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 // ---------------------------------------------------------------- host side
@@ -332,55 +597,58 @@ static EncodeTiledFn encode_fn()
 
 struct MapKey {
     const void *ptr;
-    int cin, stride, H, W, bw, bh;
+    int c, stride, H, W, bw, bh;
     bool operator==(const MapKey &o) const
     {
-        return ptr == o.ptr && cin == o.cin && stride == o.stride && H == o.H && W == o.W && bw == o.bw && bh == o.bh;
+        return ptr == o.ptr && c == o.c && stride == o.stride && H == o.H && W == o.W && bw == o.bw && bh == o.bh;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey &k) const
     {
         size_t h = (size_t)k.ptr;
-        const int v[6] = {k.cin, k.stride, k.H, k.W, k.bw, k.bh};
+        const int v[6] = {k.c, k.stride, k.H, k.W, k.bw, k.bh};
         for (int i = 0; i < 6; ++i) h = h * 1000003u ^ (size_t)v[i];
         return h;
     }
 };
 
-// (C, W, H) view of a pixel-major fp32 activation buffer; box = (32 channels, bw, bh), 128-byte swizzle,
-// out-of-bounds elements (padding, channel tail, image border) read as zero.
-static int activation_map(const float *in, int cin, int stride, int H, int W, int bw, int bh, CUtensorMap *out)
+// (C, W, H) view of a pixel-major fp32 buffer with `c` visible channels; box = (32, bw, bh), 128-byte
+// swizzle.  Loads read zeros outside the view, stores drop what falls outside.
+static int pixel_map(const float *ptr, int c, int stride, int H, int W, int bw, int bh, CUtensorMap *out)
 {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    const MapKey key{in, cin, stride, H, W, bw, bh};
+    const MapKey key{ptr, c, stride, H, W, bw, bh};
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it != cache.end()) { *out = it->second; return 0; }
     EncodeTiledFn enc = encode_fn();
     if (!enc) return (int)cudaErrorNotSupported;
-    const cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H};
+    const cuuint64_t dims[3] = {(cuuint64_t)c, (cuuint64_t)W, (cuuint64_t)H};
     const cuuint64_t strides[2] = {(cuuint64_t)stride * 4u, (cuuint64_t)stride * 4u * (cuuint64_t)W};
     const cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)bw, (cuuint32_t)bh};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUtensorMap m;
-    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(in), dims, strides, box, estr,
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(ptr), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return OJDF_ERR_BADARG;
-    if (cache.size() > 4096) cache.clear();
+    if (cache.size() > 8192) cache.clear();
     cache.emplace(key, m);
     *out = m;
     return 0;
 }
 
-static void layout(int cout, int *npad, int *groups)
+static int sm_count()
 {
-    const int g = (cout + 127) / 128;
-    const int per = (cout + g - 1) / g;
-    *groups = g;
-    *npad = (per + 15) / 16 * 16;
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    }
+    return n;
 }
 
 }  // namespace tc
@@ -388,29 +656,49 @@ static void layout(int cout, int *npad, int *groups)
 
 using namespace ojdf;
 
-extern "C" int ojdf_conv_tc_layout(int cout, int *npad, int *groups)
+
+// Channel-group layout: by default one group of round_up(cout,16) <= 128 columns (or ceil(cout/128) equal
+// groups); `npad_req` (multiple of 16, <= 128) forces narrower groups -- more CTAs for the small feature
+// maps of AdapNet++ where the pixels alone cannot fill the SMs.
+static void tc_layout(int cout, int npad_req, int *npad, int *groups)
+{
+    if (npad_req >= 16 && npad_req <= 128 && !(npad_req & 15)) {
+        *npad = npad_req < ((cout + 15) & ~15) ? npad_req : ((cout + 15) & ~15);
+        *groups = (cout + *npad - 1) / *npad;
+        return;
+    }
+    const int g = (cout + 127) / 128;
+    const int per = (cout + g - 1) / g;
+    *groups = g;
+    *npad = (per + 15) / 16 * 16;
+}
+
+extern "C" int ojdf_conv_tc_layout(int cout, int npad_req, int *npad, int *groups)
 {
     if (cout < 1 || !npad || !groups) return OJDF_ERR_BADARG;
-    tc::layout(cout, npad, groups);
+    tc_layout(cout, npad_req, npad, groups);
     return 0;
 }
 
-extern "C" size_t ojdf_conv_tc_weight_floats(int cin, int cout, int taps)
+extern "C" size_t ojdf_conv_tc_weight_floats(int cin, int cout, int taps, int npad_req)
 {
     if (cin < 1 || cout < 1 || taps < 1) return 0;
     int npad, groups;
-    tc::layout(cout, &npad, &groups);
+    tc_layout(cout, npad_req, &npad, &groups);
     const int nkc = (cin + tc::kBK - 1) / tc::kBK;
     return (size_t)groups * taps * nkc * 2 * npad * tc::kBK;
 }
 
-extern "C" int ojdf_conv_tc_pack_weights(const float *w_host, int cin, int cout, int taps, float *packed_host)
+// Packed weights: [group][tap][K chunk of 32][hi | lo][npad rows][32 floats]; every [npad][32] block is a
+// ready-made K-major SWIZZLE_128B shared-memory image (16-byte chunk c of row r stored at chunk c ^ (r & 7)),
+// hi = w with the low 13 mantissa bits cleared (exactly representable in tf32), lo = w - hi.
+extern "C" int ojdf_conv_tc_pack_weights(const float *w_host, int cin, int cout, int taps, int npad_req, float *packed_host)
 {
     if (!w_host || !packed_host || cin < 1 || cout < 1 || taps < 1) return OJDF_ERR_BADARG;
     int npad, groups;
-    tc::layout(cout, &npad, &groups);
+    tc_layout(cout, npad_req, &npad, &groups);
     const int nkc = (cin + tc::kBK - 1) / tc::kBK;
-    memset(packed_host, 0, ojdf_conv_tc_weight_floats(cin, cout, taps) * sizeof(float));
+    memset(packed_host, 0, ojdf_conv_tc_weight_floats(cin, cout, taps, npad_req) * sizeof(float));
     for (int g = 0; g < groups; ++g)
         for (int tap = 0; tap < taps; ++tap)
             for (int kc = 0; kc < nkc; ++kc) {
@@ -428,7 +716,6 @@ extern "C" int ojdf_conv_tc_pack_weights(const float *w_host, int cin, int cout,
                         float hi;
                         memcpy(&hi, &bits, 4);
                         const float lo = w - hi;
-                        // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
                         const int chunk = (k >> 2) ^ (r & 7);
                         const size_t off = (size_t)r * tc::kBK + chunk * 4 + (k & 3);
                         img[off] = hi;
@@ -439,8 +726,17 @@ extern "C" int ojdf_conv_tc_pack_weights(const float *w_host, int cin, int cout,
     return 0;
 }
 
+// Debug aid (not part of include/ojdf.h): read and clear the role profile filled by launches with flag 128.
+extern "C" int ojdf_conv_tc_profile(long long *out_host32)
+{
+    long long zero[32] = {0};
+    cudaError_t e = cudaMemcpyFromSymbol(out_host32, tc::g_prof, sizeof(zero));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(tc::g_prof, zero, sizeof(zero));
+    return (int)e;
+}
+
 extern "C" int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H,
-                                    int W, int taps, int act, float slope, float out_mul, int flags, void *stream)
+                                    int W, int taps, int act, float slope, float out_mul, int npad_req, int flags, void *stream)
 {
     if (!problems_host || n_problems < 1 || n_problems > tc::kMaxBatch || cin < 1 || cout < 1 || H < 1 || W < 1 ||
         H > 32767 || W > 32767 || (taps != 1 && taps != 9) || act < 0 || act > 4)
@@ -448,44 +744,107 @@ extern "C" int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int 
     tc::Params prm;
     memset(&prm, 0, sizeof(prm));
     int npad, groups;
-    tc::layout(cout, &npad, &groups);
-    // tile rectangle: 128 pixels, as wide as the image allows (16 columns by default)
-    int bw = 16, bh = 8;
-    if (W <= 8) { bw = 8; bh = 16; }
+    tc_layout(cout, npad_req, &npad, &groups);
     prm.H = H; prm.W = W; prm.cin = cin; prm.cout = cout; prm.taps = taps; prm.act = act; prm.npad = npad;
+    prm.groups = groups; prm.nprob = n_problems;
     prm.nkc = (cin + tc::kBK - 1) / tc::kBK;
-    prm.bw = bw; prm.bh = bh;
-    prm.tiles_x = (W + bw - 1) / bw;
-    prm.exact_hi = (flags & 1) ? 0 : 1;
+    prm.tiles_x = (W + tc::kBW - 1) / tc::kBW;
+    prm.tiles_y = (H + tc::kBH - 1) / tc::kBH;
     prm.slope = slope; prm.out_mul = out_mul;
-    const int tiles_y = (H + bh - 1) / bh;
+    // accumulators own 256 TMEM columns: MT M-tiles x NACC buffers x npad columns
+    if (npad <= 32) { prm.mt = 4; prm.nacc = 2; }
+    else if (npad <= 64) { prm.mt = 2; prm.nacc = 2; }
+    else { prm.mt = 2; prm.nacc = 1; }
+    if (flags & 2) prm.mt = 1;
+    if (flags & 2048) prm.nacc = 1;                           // experiment: single accumulator set, deeper A ring
+    if (prm.mt > prm.tiles_y) prm.mt = prm.tiles_y;
+    int dil = problems_host[0].dilation;
+    bool same_dil = true;
+    for (int i = 0; i < n_problems; ++i) same_dil = same_dil && problems_host[i].dilation == dil;
+    // shared-memory plan: staging slabs + weight stages + source (halo or per-tap) stages
+    const int budget = 227 * 1024 - 1024 - 2048;
+    const int stg = ((npad + 31) / 32) * tc::kSlabBytes;
+    const int b_stage = 2 * npad * 128;
+    int hd = 0;
+    if (taps == 9 && same_dil && !(flags & 4)) {
+        for (;;) {                                             // halo mode if two halo stages + two weight stages fit
+            const int rows = (tc::kBH * prm.mt + 2 * dil) * (tc::kBW + 2 * dil);
+            if (tc::kBW + 2 * dil <= 256 && tc::kBH * prm.mt + 2 * dil <= 256 &&
+                2 * ((rows * 128 + 1023) / 1024 * 1024) + 2 * b_stage + stg <= budget) { hd = dil; break; }
+            if (prm.mt == 1) break;
+            prm.mt >>= 1;
+        }
+        if (!hd) {                                             // per-tap boxes: restore the TMEM-driven MT
+            prm.mt = npad <= 32 ? 4 : 2;
+            if (prm.mt > prm.tiles_y) prm.mt = prm.tiles_y;
+        }
+    }
+    prm.hd = hd;
+    {   // TMEM: accumulators first, the rest (up to 3 x 64 columns per issuer/splitter pair) is the A ring
+        const int acc_cols = (prm.mt * prm.nacc * npad + 63) / 64 * 64;
+        prm.acol0 = acc_cols;
+        prm.a_slots = (512 - acc_cols) / 128;
+        if (prm.a_slots > tc::kAS / 2) prm.a_slots = tc::kAS / 2;
+        if (prm.a_slots < 1) return OJDF_ERR_BADARG;
+    }
+    prm.bwid = tc::kBW + 2 * hd;
+    int bhid = tc::kBH * prm.mt + 2 * hd;
+    // sub-boxes: a whole number of 1024-byte swizzle atoms each (sub_rows * bwid % 8 == 0)
+    int sub_min = 1;
+    while ((sub_min * prm.bwid) & 7) sub_min <<= 1;
+    const int sub_mul = (flags >> 12) & 15;                     // experiment knob: 0 = one TMA operation per box
+    prm.sub_rows = sub_mul ? sub_min * sub_mul : bhid;
+    if (prm.sub_rows > bhid) prm.sub_rows = bhid;
+    prm.nsub = (bhid + prm.sub_rows - 1) / prm.sub_rows;
+    bhid = prm.nsub * prm.sub_rows;                             // extra rows (if any) are loaded and never read
+    if (bhid > 256) return OJDF_ERR_BADARG;
+    prm.box_bytes = prm.bwid * bhid * 128;
+    prm.src_bytes = (prm.box_bytes + 1023) / 1024 * 1024;
+    int bs = 2, hs = 2;
+    if (hs * prm.src_bytes + bs * b_stage + stg > budget) hs = 1;
+    if (hs * prm.src_bytes + bs * b_stage + stg > budget) return OJDF_ERR_BADARG;
+    for (bool grew = true; grew;) {                             // grow the rings while they fit: weights first
+        grew = false;
+        if (bs < tc::kMaxB && hs * prm.src_bytes + (bs + 1) * b_stage + stg <= budget) { ++bs; grew = true; }
+        if (hs < tc::kMaxSrc && hs < 3 && (hs + 1) * prm.src_bytes + bs * b_stage + stg <= budget) { ++hs; grew = true; }
+    }
+    prm.src_stages = hs; prm.b_stages = bs;
+    // store mode 0: TMA store (needs 16-byte aligned channel offset and a width that is a multiple of 4, or
+    // pad channels the caller does not care about); 1: coalesced stores from the staging tile; 2: per-thread stores
+    prm.store_mode = (flags & 8) ? 2 : 0;
+    prm.dbg = flags & (16 | 32 | 64 | 128 | 256 | 512 | 1024);
     for (int i = 0; i < n_problems; ++i) {
         const ojdf_conv_problem &q = problems_host[i];
         if (!q.in_dev || !q.weights_dev || !q.scale_dev || !q.shift_dev || !q.out_dev || (q.in_stride & 3) || q.in_stride < cin ||
             ((uintptr_t)q.in_dev & 15) || ((uintptr_t)q.weights_dev & 15) || q.out_stride < q.out_coffset + cout ||
             q.out_coffset < 0 || q.dilation < 1 || (q.residual_dev && q.residual_stride < cout))
             return OJDF_ERR_BADARG;
-        const int r = tc::activation_map(q.in_dev, cin, q.in_stride, H, W, bw, bh, &prm.tmap[i]);
-        if (r) return r;
-        prm.p[i] = tc::Problem{q.weights_dev, q.scale_dev, q.shift_dev, q.out_dev, q.residual_dev,
-                               q.out_stride, q.out_coffset, q.dilation, q.residual_stride};
+        // TMA stores move whole 16-byte units: the channel offset must be a multiple of 4 and a width that is not
+        // is rounded up -- allowed only when the caller owns those pad channels (flag 1); they receive zeros
+        if (prm.store_mode == 0 && ((q.out_stride & 3) || ((uintptr_t)q.out_dev & 15) || (q.out_coffset & 3) ||
+                                    ((cout & 3) && (!(flags & 1) || q.out_coffset + ((cout + 3) & ~3) > q.out_stride))))
+            prm.store_mode = 1;
     }
-    const size_t stage_bytes = 2 * (size_t)tc::kATileBytes + 2 * (size_t)npad * 128;
-    const int n_iter = taps * prm.nkc;
-    // two CTAs per SM when two stages each fit (the epilogue of one overlaps the main loop of the other)
-    int stages = (int)((112 * 1024 - 1024) / stage_bytes);
-    if (stages < 2) stages = (int)((224 * 1024 - 1024) / stage_bytes);
-    if (stages > tc::kMaxStages) stages = tc::kMaxStages;
-    if (stages > n_iter) stages = n_iter;
-    if (stages < 1) return OJDF_ERR_BADARG;
-    prm.stages = stages;
-    const size_t smem = stages * stage_bytes + 1024;
+    for (int i = 0; i < n_problems; ++i) {
+        const ojdf_conv_problem &q = problems_host[i];
+        int r = tc::pixel_map(q.in_dev, cin, q.in_stride, H, W, prm.bwid, prm.sub_rows, &prm.in_map[i]);
+        if (r) return r;
+        if (prm.store_mode == 0) {
+            r = tc::pixel_map(q.out_dev, q.out_coffset + ((cout + 3) & ~3), q.out_stride, H, W, tc::kBW, tc::kBH, &prm.out_map[i]);
+            if (r) return r;
+        }
+        prm.p[i] = tc::Problem{q.weights_dev, q.scale_dev, q.shift_dev, q.out_dev, q.residual_dev,
+                                q.out_stride, q.out_coffset, q.dilation, q.residual_stride};
+    }
+    const size_t smem = (size_t)hs * prm.src_bytes + (size_t)bs * b_stage + stg + 1024;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256);
+        cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
         attr = true;
     }
-    dim3 grid(prm.tiles_x * tiles_y, groups, n_problems);
+    const long long total = (long long)n_problems * groups * prm.tiles_x * prm.tiles_y;
+    int grid = tc::sm_count();
+    if (grid > total) grid = (int)total;
     tc::conv_tc_kernel<<<grid, tc::kThreads, smem, (cudaStream_t)stream>>>(prm);
     return launched(1);
 }

@@ -21,9 +21,23 @@ from torch.nn import functional as F
 
 from .. import _lib
 
-from .fusion_engine import ConvProblem, _Conv as _ConvBase, _pad4
+from .fusion_engine import ConvProblem, _Conv as _ConvBase, _pad4, conv_mode
 
-_Conv = functools.partial(_ConvBase, tc=False)        # this engine still runs the fp32 FMA kernels
+_TAIL_PIXELS = 300          # 15 x 20: four 128-pixel M-tiles per problem
+
+
+def _npad_for(cout, n_problems, n_tiles=4):
+    """Output-channel group width of the tensor-core kernel on the small tail maps: the widest of
+    128 / 64 / 32 that still yields ~one CTA per SM (tiles x groups x problems >= 120)."""
+    for npad in (128, 64, 32):
+        if n_tiles * n_problems * ((cout + npad - 1) // npad) >= 120:
+            return npad
+    return 32
+
+
+def _Conv(conv, bn, act, device, n_problems=2, **kw):
+    tc = conv_mode() == 'tc'
+    return _ConvBase(conv, bn, act, device, tc=tc, npad_req=_npad_for(conv.out_channels, n_problems) if tc else 0, **kw)
 
 
 class _Unit:
@@ -33,7 +47,7 @@ class _Unit:
         self.ssma = hasattr(m, 'conv2a')
         self.c1 = _Conv(m.conv1, m.bn1, 'relu', device)
         if self.ssma:
-            self.c2 = [_Conv(m.conv2a, m.bn2a, 'relu', device), _Conv(m.conv2b, m.bn2b, 'relu', device)]
+            self.c2 = [_Conv(m.conv2a, m.bn2a, 'relu', device, n_problems=4), _Conv(m.conv2b, m.bn2b, 'relu', device, n_problems=4)]
             self.dropout = bool(m.dropout)
         else:
             self.c2 = [_Conv(m.conv2, m.bn2, 'relu', device)]
@@ -50,8 +64,9 @@ class _Unit:
 class _ASPP:
     def __init__(self, m, device):
         self.b1 = _Conv(m.branch1_conv, m.branch1_bn, 'relu', device)
-        self.br = [[_Conv(b[0], b[1], 'relu', device), _Conv(b[3], b[4], 'relu', device),
-                    _Conv(b[6], b[7], 'relu', device), _Conv(b[9], b[10], 'relu', device)] for b in m.branch234]
+        self.br = [[_Conv(b[0], b[1], 'relu', device, n_problems=6), _Conv(b[3], b[4], 'relu', device, n_problems=6),
+                    _Conv(b[6], b[7], 'relu', device, n_problems=6), _Conv(b[9], b[10], 'relu', device, n_problems=6)]
+                   for b in m.branch234]
         co = self.b1.cout
         self.cout, self.cin, self.mid = co, self.b1.cin, self.br[0][0].cout
         self.fin = _Conv(m.eASPP_fin_conv, m.eASPP_fin_bn, 'relu', device, cin_slice=(0, 4 * co))    # branches 1-4
@@ -84,11 +99,12 @@ class EncoderTailEngine:
         self.partial = torch.empty(self.PARTIAL_BLOCKS * 2048, dtype=torch.float32, device=dev)
         self._keep += [T1, T2, D]
         self.plan = []
+        self.tc = conv_mode() == 'tc'
 
         def conv_step(pairs):
             c0 = pairs[0][0]
             arr = (ConvProblem * len(pairs))(*[p for _, p in pairs])
-            self.plan.append(('conv', arr, len(pairs), c0.cin, c0.cout, c0.taps, c0.act, c0.slope))
+            self.plan.append(('conv', arr, len(pairs), c0.cin, c0.cout, c0.taps, c0.act, c0.slope, c0.npad_req))
 
         cur = 0
         for ui in range(len(units[0])):
@@ -144,9 +160,12 @@ class EncoderTailEngine:
             for step in self.plan:
                 kind = step[0]
                 if kind == 'conv':
-                    _, arr, n, cin, cout, taps, act, slope = step
-                    _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0,
-                                                        self.scratch.data_ptr(), self.scratch.numel() * 4, st))
+                    _, arr, n, cin, cout, taps, act, slope, npad_req = step
+                    if self.tc:
+                        _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 0, st))
+                    else:
+                        _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0,
+                                                            self.scratch.data_ptr(), self.scratch.numel() * 4, st))
                 elif kind == 'dropout':
                     for t in step[1]:                            # reference quirk: active in eval mode
                         t.copy_(F.dropout(t, p=0.5, training=True))

@@ -48,14 +48,14 @@ def conv_mode():
     return m
 
 
-def pack_tc_weights(w):
+def pack_tc_weights(w, npad_req=0):
     """(cout, cin, kh, kw) f64/f32 host tensor -> packed float32 image for ojdf_conv_tc_batched."""
     cout, cin, kh, kw = w.shape
     taps = kh * kw
     L = _lib.lib()
     src = np.ascontiguousarray(w.float().numpy().reshape(cout, cin, taps))
-    out = np.zeros(L.ojdf_conv_tc_weight_floats(cin, cout, taps), np.float32)
-    _lib.check(L.ojdf_conv_tc_pack_weights(src.ctypes.data, cin, cout, taps, out.ctypes.data))
+    out = np.zeros(L.ojdf_conv_tc_weight_floats(cin, cout, taps, npad_req), np.float32)
+    _lib.check(L.ojdf_conv_tc_pack_weights(src.ctypes.data, cin, cout, taps, npad_req, out.ctypes.data))
     return torch.from_numpy(out)
 
 
@@ -69,7 +69,7 @@ class ConvProblem(C.Structure):
 class _Conv:
     """One fused conv (+BN) (+activation): weights re-laid out for conv_tile_kernel."""
 
-    def __init__(self, conv, bn, act, device, cin_slice=None, slope=0.01, tc=None, cin_map=None):
+    def __init__(self, conv, bn, act, device, cin_slice=None, slope=0.01, tc=None, cin_map=None, npad_req=0):
         w = conv.weight.detach().double().cpu()                 # (cout, cin, kh, kw); all folding on the host in f64
         if cin_slice is not None:
             w = w[:, cin_slice[0]:cin_slice[1]]
@@ -97,7 +97,8 @@ class _Conv:
         else:
             s, t = torch.ones(cout, dtype=torch.float64), bias
         self.weights = prep.float().contiguous().to(device)
-        self.weights_tc = pack_tc_weights(w).to(device) if (conv_mode() == 'tc' if tc is None else tc) else None
+        self.npad_req = int(npad_req)
+        self.weights_tc = pack_tc_weights(w, self.npad_req).to(device) if (conv_mode() == 'tc' if tc is None else tc) else None
         self.scale = s.float().contiguous().to(device)
         self.shift = t.float().contiguous().to(device)
         self.act, self.slope = _ACT[act], float(slope)
@@ -267,7 +268,7 @@ class FusionNetEngine:
                     _, arr, n, cin, cout, taps, act, slope = step[:8]
                     out_mul = step[8] if len(step) > 8 else 1.0
                     if self.tc:
-                        _lib.check(L.ojdf_conv_tc2_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, 1, st))   # 1: pads are ours
+                        _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, 0, 1, st))   # 1: pads are ours
                     else:
                         _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, None, 0, st))
                 elif kind == 'pool':

@@ -77,3 +77,34 @@ def test_host_modules_refuse_cpu_tensors():
     integ = Integrator(cfg)
     with pytest.raises(_lib.OjdfError):
         integ.forward({}, vol, vol, vol, vol.to(torch.uint8))
+
+
+def test_conv_tc_weight_packing_layout(L):
+    """ojdf_conv_tc_pack_weights against a numpy restatement of its documented layout:
+    [group][tap][K chunk of 32][hi|lo][npad][32], 16-byte chunk c of row r stored at chunk c ^ (r & 7),
+    hi = w with the low 13 mantissa bits cleared, lo = w - hi."""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    for cin, cout, taps, npad_req in ((19, 19, 9, 0), (114, 95, 1, 0), (70, 300, 1, 0), (40, 256, 9, 32)):
+        npad, groups = C.c_int(), C.c_int()
+        assert L.ojdf_conv_tc_layout(cout, npad_req, C.byref(npad), C.byref(groups)) == 0
+        npad, groups = npad.value, groups.value
+        assert npad % 16 == 0 and npad <= 128 and npad * groups >= cout
+        w = rng.standard_normal((cout, cin, taps)).astype(np.float32)
+        n = L.ojdf_conv_tc_weight_floats(cin, cout, taps, npad_req)
+        nkc = (cin + 31) // 32
+        assert n == groups * taps * nkc * 2 * npad * 32
+        packed = np.full(n, np.nan, np.float32)
+        assert L.ojdf_conv_tc_pack_weights(w.ctypes.data, cin, cout, taps, npad_req, packed.ctypes.data) == 0
+        img = packed.reshape(groups, taps, nkc, 2, npad, 8, 4)
+        hi = (w.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        lo = w - hi
+        assert np.array_equal(hi + lo, w)
+        for _ in range(200):
+            co, ci, t = int(rng.integers(cout)), int(rng.integers(cin)), int(rng.integers(taps))
+            g, r, kc, k = co // npad, co % npad, ci // 32, ci % 32
+            chunk = (k >> 2) ^ (r & 7)
+            assert img[g, t, kc, 0, r, chunk, k & 3] == hi[co, ci, t]
+            assert img[g, t, kc, 1, r, chunk, k & 3] == lo[co, ci, t]
+        assert np.count_nonzero(packed) <= 2 * w.size and not np.isnan(packed).any()
+    assert L.ojdf_conv_tc_batched(None, 1, 32, 32, 8, 16, 1, 0, 0.0, 1.0, 0, 0, None) == -1
