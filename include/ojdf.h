@@ -140,6 +140,9 @@ typedef struct ojdf_conv_problem {
     float *out_dev;
     const float *residual_dev;      /* optional (H*W, residual_stride): added before the activation */
     int in_stride, out_stride, out_coffset, dilation, residual_stride;
+    int in_step;                    /* tensor-core kernel only: 0/1 = dense, 2 = read every other input pixel of every
+                                     * other row (stride-2 1x1 convolutions, ResNet down-sampling); H, W stay OUTPUT sizes */
+    int in_width;                   /* pixels per input row when in_step > 1 (the input image is in_width wide) */
 } ojdf_conv_problem;
 /* act additionally accepts 4 = sigmoid.  scratch_dev (optional, scratch_bytes): when the pixel count
  * alone cannot fill the GPU (AdapNet++'s 15x20 maps) the K loop is split across blocks, partial sums go

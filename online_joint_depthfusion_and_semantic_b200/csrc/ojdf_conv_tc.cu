@@ -598,9 +598,11 @@ static EncodeTiledFn encode_fn()
 struct MapKey {
     const void *ptr;
     int c, stride, H, W, bw, bh;
+    long long row_stride;
     bool operator==(const MapKey &o) const
     {
-        return ptr == o.ptr && c == o.c && stride == o.stride && H == o.H && W == o.W && bw == o.bw && bh == o.bh;
+        return ptr == o.ptr && c == o.c && stride == o.stride && H == o.H && W == o.W && bw == o.bw && bh == o.bh &&
+               row_stride == o.row_stride;
     }
 };
 struct MapKeyHash {
@@ -615,18 +617,20 @@ struct MapKeyHash {
 
 // (C, W, H) view of a pixel-major fp32 buffer with `c` visible channels; box = (32, bw, bh), 128-byte
 // swizzle.  Loads read zeros outside the view, stores drop what falls outside.
-static int pixel_map(const float *ptr, int c, int stride, int H, int W, int bw, int bh, CUtensorMap *out)
+// `stride` = floats between consecutive pixels of the view, `row_stride` = floats between its rows (0: W * stride).
+static int pixel_map(const float *ptr, int c, int stride, int H, int W, int bw, int bh, CUtensorMap *out, long long row_stride = 0)
 {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    const MapKey key{ptr, c, stride, H, W, bw, bh};
+    if (!row_stride) row_stride = (long long)W * stride;
+    const MapKey key{ptr, c, stride, H, W, bw, bh, row_stride};
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it != cache.end()) { *out = it->second; return 0; }
     EncodeTiledFn enc = encode_fn();
     if (!enc) return (int)cudaErrorNotSupported;
     const cuuint64_t dims[3] = {(cuuint64_t)c, (cuuint64_t)W, (cuuint64_t)H};
-    const cuuint64_t strides[2] = {(cuuint64_t)stride * 4u, (cuuint64_t)stride * 4u * (cuuint64_t)W};
+    const cuuint64_t strides[2] = {(cuuint64_t)stride * 4u, (cuuint64_t)row_stride * 4u};
     const cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)bw, (cuuint32_t)bh};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUtensorMap m;
@@ -827,7 +831,10 @@ extern "C" int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int 
     }
     for (int i = 0; i < n_problems; ++i) {
         const ojdf_conv_problem &q = problems_host[i];
-        int r = tc::pixel_map(q.in_dev, cin, q.in_stride, H, W, prm.bwid, prm.sub_rows, &prm.in_map[i]);
+        const int step = q.in_step > 1 ? q.in_step : 1;
+        if (step > 1 && (step != 2 || q.in_width < (W - 1) * step + 1)) return OJDF_ERR_BADARG;
+        int r = tc::pixel_map(q.in_dev, cin, q.in_stride * step, H, W, prm.bwid, prm.sub_rows, &prm.in_map[i],
+                              step > 1 ? (long long)q.in_stride * q.in_width * step : 0);
         if (r) return r;
         if (prm.store_mode == 0) {
             r = tc::pixel_map(q.out_dev, q.out_coffset + ((cout + 3) & ~3), q.out_stride, H, W, tc::kBW, tc::kBH, &prm.out_map[i]);

@@ -207,24 +207,30 @@ class AdapNet(nn.Module):
 
     def no_resn50_dropout(self):
         """Reference helper (modules/adapnet.py:386-388): only layer3[2] of both encoders."""
-        self._engine = None
+        self._drop_engines()
         self.encoder_mod1.res_n50_enc.layer3[2].dropout = False
         self.encoder_mod2.res_n50_enc.layer3[2].dropout = False
 
     # ---- libojdf engine for the 15x20 tail (adapnet_engine.py); same invalidation rules as FusionNet
     _engine = None
+    _full_engine = None
     use_engine = True
+    whole_engine = True         # False: only the 15x20 tail runs on libojdf, the rest on the library
+
+    def _drop_engines(self):
+        self._engine = None
+        self._full_engine = None
 
     def train(self, mode=True):
-        self._engine = None
+        self._drop_engines()
         return super().train(mode)
 
     def _apply(self, fn, *a, **k):
-        self._engine = None
+        self._drop_engines()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._engine = None
+        self._drop_engines()
         return super().load_state_dict(*a, **k)
 
     def engine_ready(self, x):
@@ -242,13 +248,24 @@ class AdapNet(nn.Module):
 
     def set_bottleneck_dropout(self, enabled):
         """Switch the eval-time-active dropout of every multi-scale unit (deterministic runs)."""
-        self._engine = None
+        self._drop_engines()
         for m in self.modules():
             if isinstance(m, BottleneckSSMA):
                 m.dropout = bool(enabled) and m.dropout_default
         return self
 
+    def _whole(self, mod1, mod2):
+        from .adapnet_engine import AdapNetEngine
+        h, w = mod1.shape[-2:]
+        e = self._full_engine
+        if e is None or (e.h, e.w) != (h, w) or e.device != mod1.device:
+            e = self._full_engine = AdapNetEngine(self, h, w, mod1.device)
+        return e.forward(mod1, mod2)
+
     def forward(self, mod1, mod2=None):
+        from .fusion_engine import conv_mode
+        if self.engine_ready(mod1) and self.whole_engine and conv_mode() == 'tc' and mod1.shape[0] == 1:
+            return self._whole(mod1, mod2)
         if self.engine_ready(mod1):
             # front (conv1..layer3[0]) on the library, the 15x20 tail + eASPP on libojdf's kernels
             pre1, skip2, skip1 = self.encoder_mod1.forward_front(mod1)

@@ -1,4 +1,12 @@
-"""Inference engine for the low-resolution tail of AdapNet++ on libojdf's tap-GEMM kernels.
+"""Inference engines for AdapNet++ on libojdf's tap-GEMM kernels.
+
+`AdapNetEngine` (bottom of this file) runs the whole network pixel-major: everything except the 7x7 stem,
+the max-pool, the three transposed convolutions and the bilinear aux heads is a fused conv + BatchNorm +
+activation (+ residual) launch of the tensor-core kernel (csrc/ojdf_conv_tc.cu); stride-2 layers are the
+stride-1 layer followed by a consumer that reads every other pixel (`in_step = 2`).  It embeds
+`EncoderTailEngine`, described next.
+
+Low-resolution tail:
 
 At 240x320 the encoder runs layer3[1:], layer4 and the eASPP head on 15x20 feature maps with 256..2048
 channels (modules/adapnet.py:103-149,152-216).  That is 72 % of each encoder's FLOPs, and exactly the
@@ -35,9 +43,10 @@ def _npad_for(cout, n_problems, n_tiles=4):
     return 32
 
 
-def _Conv(conv, bn, act, device, n_problems=2, **kw):
+def _Conv(conv, bn, act, device, n_problems=2, n_tiles=4, **kw):
     tc = conv_mode() == 'tc'
-    return _ConvBase(conv, bn, act, device, tc=tc, npad_req=_npad_for(conv.out_channels, n_problems) if tc else 0, **kw)
+    return _ConvBase(conv, bn, act, device, tc=tc,
+                     npad_req=_npad_for(conv.out_channels, n_problems, n_tiles) if tc else 0, **kw)
 
 
 class _Unit:
@@ -82,8 +91,9 @@ class EncoderTailEngine:
     SCRATCH_BYTES = 96 << 20
     PARTIAL_BLOCKS = 296
 
-    def __init__(self, encoders, aspps, h, w, device):
-        """encoders: [Encoder, ...] (1 or 2), aspps: matching eASPP modules; h, w: tail resolution."""
+    def __init__(self, encoders, aspps, h, w, device, out_buf=None):
+        """encoders: [Encoder, ...] (1 or 2), aspps: matching eASPP modules; h, w: tail resolution.
+        out_buf: optional (h*w, n*256) buffer the eASPP outputs are written into side by side."""
         self.h, self.w, self.N, self.device = int(h), int(w), int(h) * int(w), torch.device(device)
         dev, N, n = self.device, self.N, len(encoders)
         self.n = n
@@ -131,7 +141,7 @@ class EncoderTailEngine:
         co, mid = A.cout, A.mid
         cat = [z(4 * co) for _ in range(n)]
         U = [[[z(_pad4(mid)) for _ in range(2)] for _ in range(3)] for _ in range(n)]
-        self.out = [z(co) for _ in range(n)]
+        self.out = [z(co) for _ in range(n)] if out_buf is None else None
         self._keep += [cat, U]
         ms = _pad4(mid)
         for e in range(n):
@@ -142,9 +152,36 @@ class EncoderTailEngine:
         conv_step([(heads[e].br[b][2], heads[e].br[b][2].problem(U[e][b][1], ms, U[e][b][0], ms)) for e in range(n) for b in range(3)])
         conv_step([(heads[e].br[b][3], heads[e].br[b][3].problem(U[e][b][0], ms, cat[e], 4 * co, (b + 1) * co))
                    for e in range(n) for b in range(3)])
-        conv_step([(heads[e].fin, heads[e].fin.problem(cat[e], 4 * co, self.out[e], co, 0, shift=heads[e].frame_shift))
-                   for e in range(n)])
+        if out_buf is None:
+            conv_step([(heads[e].fin, heads[e].fin.problem(cat[e], 4 * co, self.out[e], co, 0, shift=heads[e].frame_shift))
+                       for e in range(n)])
+        else:
+            conv_step([(heads[e].fin, heads[e].fin.problem(cat[e], 4 * co, out_buf, n * co, e * co, shift=heads[e].frame_shift))
+                       for e in range(n)])
         self.cmax, self.cout = cmax, co
+
+    def run(self, st):
+        """Walk the plan on stream `st`; X[e][0] must hold the (N, 1024) pixel-major input of encoder e."""
+        L = _lib.lib()
+        N, H, W = self.N, self.h, self.w
+        for step in self.plan:
+            kind = step[0]
+            if kind == 'conv':
+                _, arr, n, cin, cout, taps, act, slope, npad_req = step
+                if self.tc:
+                    _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 0, st))
+                else:
+                    _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0,
+                                                        self.scratch.data_ptr(), self.scratch.numel() * 4, st))
+            elif kind == 'dropout':
+                for t in step[1]:                            # reference quirk: active in eval mode
+                    t.copy_(F.dropout(t, p=0.5, training=True))
+            else:
+                _, a, src, ss = step
+                _lib.check(L.ojdf_gap_bias(src.data_ptr(), ss, N, a.cin, a.wg.data_ptr(), a.g_scale.data_ptr(),
+                                           a.g_shift.data_ptr(), a.cout, 1, a.wf5.data_ptr(), a.fin.scale.data_ptr(),
+                                           a.fin.shift.data_ptr(), a.cout, self.partial.data_ptr(), self.PARTIAL_BLOCKS,
+                                           a.frame_shift.data_ptr(), st))
 
     def forward(self, xs):
         """xs: list of (1, C, h, w) NCHW tensors (output of layer3[0] of each encoder).
@@ -157,26 +194,216 @@ class EncoderTailEngine:
             for e, x in enumerate(xs):
                 x = x.detach().float().contiguous()
                 _lib.check(L.ojdf_nchw_to_nhwc(x.data_ptr(), self.cin0, N, self.X[e][0].data_ptr(), self.cmax, 0, st))
-            for step in self.plan:
-                kind = step[0]
-                if kind == 'conv':
-                    _, arr, n, cin, cout, taps, act, slope, npad_req = step
-                    if self.tc:
-                        _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 0, st))
-                    else:
-                        _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0,
-                                                            self.scratch.data_ptr(), self.scratch.numel() * 4, st))
-                elif kind == 'dropout':
-                    for t in step[1]:                            # reference quirk: active in eval mode
-                        t.copy_(F.dropout(t, p=0.5, training=True))
-                else:
-                    _, a, src, ss = step
-                    _lib.check(L.ojdf_gap_bias(src.data_ptr(), ss, N, a.cin, a.wg.data_ptr(), a.g_scale.data_ptr(),
-                                               a.g_shift.data_ptr(), a.cout, 1, a.wf5.data_ptr(), a.fin.scale.data_ptr(),
-                                               a.fin.shift.data_ptr(), a.cout, self.partial.data_ptr(), self.PARTIAL_BLOCKS,
-                                               a.frame_shift.data_ptr(), st))
+            self.run(st)
             for e in range(self.n):
                 o = torch.empty(1, self.cout, H, W, dtype=torch.float32, device=dev)
                 _lib.check(L.ojdf_nhwc_to_nchw(self.out[e].data_ptr(), self.cout, 0, self.cout, N, o.data_ptr(), st))
                 outs.append(o)
         return outs
+
+
+class AdapNetEngine:
+    """Whole-network launch plan (stage 1 or 2) at input size (h, w), h and w multiples of 16."""
+
+    def __init__(self, net, h, w, device):
+        assert h % 16 == 0 and w % 16 == 0, 'AdapNet++ needs h, w = 0 mod 16 (modules/adapnet.py:288)'
+        self.h, self.w, self.device = int(h), int(w), torch.device(device)
+        dev = self.device
+        self.net = net
+        self.stage2 = net.stage != 1
+        encs = [net.encoder_mod1] + ([net.encoder_mod2] if self.stage2 else [])
+        aspps = [net.eASPP_mod1, net.eASPP_mod2] if self.stage2 else [net.eASPP]
+        n = self.n = len(encs)
+        (H4, W4), (H8, W8), (H16, W16) = (h // 4, w // 4), (h // 8, w // 8), (h // 16, w // 16)
+        N4, N8, N16 = H4 * W4, H8 * W8, H16 * W16
+        self.dims = (H4, W4, H8, W8, H16, W16)
+        self.tc = conv_mode() == 'tc'
+        if not self.tc:
+            raise NotImplementedError('the whole-network engine needs the tensor-core kernel (strided reads)')
+        self._keep, self.plan = [], []
+        plan = self.plan
+
+        def z(npix, c):
+            """Every buffer the plan points at by raw address stays owned by the engine."""
+            t = torch.zeros(npix, c, dtype=torch.float32, device=dev)
+            self._keep.append(t)
+            return t
+
+        def tiles(H, W):
+            return ((H + 7) // 8) * ((W + 15) // 16)
+
+        def conv_step(pairs, H, W):
+            c0 = pairs[0][0]
+            arr = (ConvProblem * len(pairs))(*[p for _, p in pairs])
+            self._keep.append([c for c, _ in pairs])
+            plan.append(('conv', arr, len(pairs), c0.cin, c0.cout, H, W, c0.taps, c0.act, c0.slope, c0.npad_req))
+
+        def mk(conv, bn, act, H, W, n_problems=n, **kw):
+            return _Conv(conv, bn, act, dev, n_problems=n_problems, n_tiles=tiles(H, W), **kw)
+
+        def unit(ms, src, src_stride, Hin, Win, dst, dst_stride):
+            """One residual unit (torchvision Bottleneck or BottleneckSSMA) of every encoder in lock step.
+            src/dst: per-encoder buffers.  A stride-2 unit computes its 3x3 at the input resolution and lets
+            conv3 / the shortcut read every other pixel."""
+            m0 = ms[0]
+            ssma = hasattr(m0, 'conv2a')
+            stride = 1 if ssma else int(m0.conv2.stride[0])
+            Ho, Wo = Hin // stride, Win // stride
+            Nin = Hin * Win
+            mid = m0.conv1.out_channels
+            c1 = [mk(m.conv1, m.bn1, 'relu', Hin, Win) for m in ms]
+            T1 = [z(Nin, mid) for _ in ms]
+            conv_step([(c1[e], c1[e].problem(src[e], src_stride, T1[e], mid)) for e in range(n)], Hin, Win)
+            if ssma:
+                half = m0.conv2a.out_channels
+                c2 = [[mk(m.conv2a, m.bn2a, 'relu', Hin, Win, 2 * n), mk(m.conv2b, m.bn2b, 'relu', Hin, Win, 2 * n)] for m in ms]
+                T2 = [z(Nin, 2 * half) for _ in ms]
+                conv_step([(c2[e][k], c2[e][k].problem(T1[e], mid, T2[e], 2 * half, k * half)) for e in range(n) for k in range(2)],
+                          Hin, Win)
+                mid2 = 2 * half
+            else:
+                c2 = [mk(m.conv2, m.bn2, 'relu', Hin, Win) for m in ms]
+                T2 = [z(Nin, mid) for _ in ms]
+                conv_step([(c2[e], c2[e].problem(T1[e], mid, T2[e], mid)) for e in range(n)], Hin, Win)
+                mid2 = mid
+            step_kw = dict(in_step=2, in_width=Win) if stride == 2 else {}
+            cout = m0.conv3.out_channels
+            if m0.downsample is not None:
+                assert int(m0.downsample[0].stride[0]) == stride
+                dn = [mk(m.downsample[0], m.downsample[1], 'none', Ho, Wo) for m in ms]
+                D = [z(Ho * Wo, cout) for _ in ms]
+                conv_step([(dn[e], dn[e].problem(src[e], src_stride, D[e], cout, **step_kw)) for e in range(n)], Ho, Wo)
+                res, res_stride = D, cout
+            else:
+                assert stride == 1
+                res, res_stride = src, src_stride
+            c3 = [mk(m.conv3, m.bn3, 'relu', Ho, Wo) for m in ms]
+            conv_step([(c3[e], c3[e].problem(T2[e], mid2, dst[e], dst_stride, 0, residual=res[e], residual_stride=res_stride,
+                                             **step_kw)) for e in range(n)], Ho, Wo)
+            self._keep += [T1, T2, res]
+            if ssma and m0.dropout:
+                plan.append(('dropout', [dst[e][:, :cout] for e in range(n)]))
+            return Ho, Wo
+
+        # ---- encoders: stem (library) -> layer1 -> skip2 -> layer2 -> skip1 -> layer3[0] -> tail engine
+        self.S0 = [z(N4, 64) for _ in range(n)]
+        self.FX = z(N16, n * 256)                              # eASPP outputs of all encoders side by side
+        self.tail = EncoderTailEngine(encs, aspps, H16, W16, dev, out_buf=self.FX)
+        cur, cs = self.S0, 64
+        for ui in range(len(encs[0].res_n50_enc.layer1)):
+            ms = [e.res_n50_enc.layer1[ui] for e in encs]
+            dst = [z(N4, 256) for _ in range(n)]
+            unit(ms, cur, cs, H4, W4, dst, 256)
+            cur, cs = dst, 256
+        self.L1 = cur
+        self.SK2 = z(N4, n * 24)                               # skip connections of all encoders side by side
+        sk2 = [mk(e.enc_skip2_conv, e.enc_skip2_conv_bn, 'none', H4, W4) for e in encs]
+        conv_step([(sk2[e], sk2[e].problem(cur[e], cs, self.SK2, n * 24, e * 24)) for e in range(n)], H4, W4)
+        Hc, Wc = H4, W4
+        for ui in range(len(encs[0].res_n50_enc.layer2)):
+            ms = [e.res_n50_enc.layer2[ui] for e in encs]
+            st = 1 if hasattr(ms[0], 'conv2a') else int(ms[0].conv2.stride[0])
+            dst = [z((Hc // st) * (Wc // st), 512) for _ in range(n)]
+            Hc, Wc = unit(ms, cur, cs, Hc, Wc, dst, 512)
+            cur, cs = dst, 512
+        assert (Hc, Wc) == (H8, W8)
+        self.L2 = cur
+        self.SK1 = z(N8, n * 24)
+        sk1 = [mk(e.enc_skip1_conv, e.enc_skip1_conv_bn, 'none', H8, W8) for e in encs]
+        conv_step([(sk1[e], sk1[e].problem(cur[e], cs, self.SK1, n * 24, e * 24)) for e in range(n)], H8, W8)
+        ms = [e.res_n50_enc.layer3[0] for e in encs]
+        unit(ms, cur, cs, H8, W8, [self.tail.X[e][0] for e in range(n)], self.tail.cmax)
+        plan.append(('tail',))
+
+        # ---- SSMA fusion of the two modalities (stage 2): cat -> 3x3 relu -> 3x3 sigmoid -> gate -> 3x3 + BN
+        def ssma(m, cat, N, H, W, feat):
+            red = m.link[0].out_channels
+            l0, l1 = mk(m.link[0], None, 'relu', H, W, 1), mk(m.link[2], None, 'sigmoid', H, W, 1)
+            fin = mk(m.final_conv[0], m.final_conv[1], 'none', H, W, 1)
+            G, GATE, out = z(N, _pad4(red)), z(N, 2 * feat), z(N, feat)
+            conv_step([(l0, l0.problem(cat, 2 * feat, G, _pad4(red)))], H, W)
+            conv_step([(l1, l1.problem(G, _pad4(red), GATE, 2 * feat))], H, W)
+            plan.append(('mul', GATE, cat))
+            conv_step([(fin, fin.problem(GATE, 2 * feat, out, feat))], H, W)
+            return out
+
+        d = net.decoder
+        C = int(d.n_classes)
+        if self.stage2:
+            self.skip2 = ssma(net.ssma_s2, self.SK2, N4, H4, W4, 24)
+            self.skip1 = ssma(net.ssma_s1, self.SK1, N8, H8, W8, 24)
+            self.X16 = ssma(net.ssma_res, self.FX, N16, H16, W16, 256)
+        else:
+            self.skip2, self.skip1, self.X16 = self.SK2, self.SK1, self.FX
+        # ---- decoder: transposed convolutions / aux heads stay on the library, on channels-last views
+        self.J1, self.J2 = z(N8, 280), z(N4, 280)
+        plan.append(('deconv1',))
+        s2a, s2b = mk(d.stage2[0], d.stage2[1], 'relu', H8, W8, 1), mk(d.stage2[3], d.stage2[4], 'relu', H8, W8, 1)
+        self.U1, self.U2 = z(N8, 256), z(N8, 256)
+        conv_step([(s2a, s2a.problem(self.J1, 280, self.U1, 256))], H8, W8)
+        conv_step([(s2b, s2b.problem(self.U1, 256, self.U2, 256))], H8, W8)
+        plan.append(('deconv2',))
+        s3a, s3b = mk(d.stage3[0], d.stage3[1], 'relu', H4, W4, 1), mk(d.stage3[3], d.stage3[4], 'relu', H4, W4, 1)
+        s3c = mk(d.stage3[6], d.stage3[7], 'none', H4, W4, 1)
+        Cp = _pad4(C)
+        self.V1, self.V2, self.V3 = z(N4, 256), z(N4, 256), z(N4, Cp)
+        self.Cp = Cp
+        conv_step([(s3a, s3a.problem(self.J2, 280, self.V1, 256))], H4, W4)
+        conv_step([(s3b, s3b.problem(self.V1, 256, self.V2, 256))], H4, W4)
+        conv_step([(s3c, s3c.problem(self.V2, 256, self.V3, Cp))], H4, W4)
+        plan.append(('deconv3',))
+
+    @staticmethod
+    def _nchw(buf, H, W, c0=0, c1=None):
+        """(1, C, H, W) channels-last view of channels [c0, c1) of a pixel-major buffer."""
+        v = buf.view(1, H, W, buf.shape[1])
+        return v[..., c0:c1].permute(0, 3, 1, 2)
+
+    def forward(self, mod1, mod2=None):
+        net, d, dev = self.net, self.net.decoder, self.device
+        H4, W4, H8, W8, H16, W16 = self.dims
+        L = _lib.lib()
+        aux = {}
+        with torch.cuda.device(dev), _lib.timed('adapnet_engine', dev):
+            st = _lib.stream_ptr(dev)
+            encs = [net.encoder_mod1] + ([net.encoder_mod2] if self.stage2 else [])
+            for e, (enc, x) in enumerate(zip(encs, [mod1, mod2][:self.n])):
+                r = enc.res_n50_enc
+                y = r.maxpool(r.relu(r.bn1(r.conv1(x.float())))).contiguous()
+                _lib.check(L.ojdf_nchw_to_nhwc(y.data_ptr(), 64, H4 * W4, self.S0[e].data_ptr(), 64, 0, st))
+            for step in self.plan:
+                kind = step[0]
+                if kind == 'conv':
+                    _, arr, n, cin, cout, H, W, taps, act, slope, npad_req = step
+                    _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 1, st))
+                elif kind == 'tail':
+                    self.tail.run(st)
+                elif kind == 'dropout':
+                    for t in step[1]:                            # reference quirk: active in eval mode
+                        t.copy_(F.dropout(t, p=0.5, training=True))
+                elif kind == 'mul':
+                    step[1].mul_(step[2])                        # gate * concatenated features (modules/adapnet.py:352)
+                elif kind == 'deconv1':
+                    x = torch.relu(d.deconv1_bn(d.deconv1(self._nchw(self.X16, H16, W16))))
+                    aux['y1'] = d._aux(x, d.aux_conv1, d.aux_conv1_bn, 8)
+                    self._join(x, self.skip1, d.fuse_conv1, self.J1, H8, W8)
+                elif kind == 'deconv2':
+                    x = d.stage2[7](d.stage2[6](self._nchw(self.U2, H8, W8)))
+                    aux['y2'] = d._aux(x, d.aux_conv2, d.aux_conv2_bn, 4)
+                    self._join(x, self.skip2, d.fuse_conv2, self.J2, H4, W4)
+                else:                                            # deconv3: x4 transposed convolution + BN on the logits
+                    C = int(d.n_classes)
+                    res = d.stage3[9](d.stage3[8](self._nchw(self.V3, H4, W4, 0, C)))
+        return [res, aux['y1'], aux['y2']]
+
+    def _join(self, x, skip, conv, J, H, W):
+        """Decoder._join (modules/adapnet.py:305-315): [x | gate * skip] into the 280-channel buffer J."""
+        d = self.net.decoder
+        Jv = J.view(1, H, W, 280)
+        Jv[..., :256].copy_(x.permute(0, 2, 3, 1))
+        sk = skip.view(1, H, W, 24)
+        if d.fusion:
+            gate = torch.relu(conv(F.adaptive_avg_pool2d(x, 1))).reshape(1, 1, 1, 24)
+            Jv[..., 256:].copy_(sk * gate)
+        else:
+            Jv[..., 256:].copy_(sk)

@@ -1,5 +1,5 @@
-"""AdapNet++ with its 15x20 tail on libojdf's kernels vs the plain PyTorch fp32 forward of the same
-module (bit-identical to the reference's modules/adapnet.py on CPU, tests/test_networks_cpu.py).
+"""AdapNet++ on libojdf's kernels (whole-network engine, and the tail-only engine) vs the plain PyTorch fp32
+forward of the same module (bit-identical to the reference's modules/adapnet.py on CPU, tests/test_networks_cpu.py).
 Tolerance: the north star's 1e-4 relative on the semantic logits (max |a-b| <= 1e-4 * max |b|)."""
 import pytest
 import torch
@@ -25,11 +25,13 @@ def _net(stage, seed=11):
     return net.to(DEV).eval()
 
 
-@pytest.mark.parametrize('stage,h,w', [(2, 240, 320), (1, 64, 96), (2, 48, 64)])
-def test_tail_engine_matches_torch_fp32(stage, h, w):
+@pytest.mark.parametrize('stage,h,w,whole', [(2, 240, 320, True), (1, 64, 96, True), (2, 48, 64, True),
+                                              (2, 240, 320, False), (1, 64, 96, False)])
+def test_engine_matches_torch_fp32(stage, h, w, whole):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     net = _net(stage)
+    net.whole_engine = whole
     g = torch.Generator().manual_seed(3)
     x1, x2 = torch.randn(1, 3, h, w, generator=g).to(DEV), torch.randn(1, 3, h, w, generator=g).to(DEV)
     args = (x1, x2) if stage == 2 else (x1,)
@@ -39,7 +41,7 @@ def test_tail_engine_matches_torch_fp32(stage, h, w):
         net.use_engine = True
         out = net(*args)
         torch.cuda.synchronize()
-    assert net._engine is not None
+    assert (net._full_engine if whole else net._engine) is not None
     for a, b in zip(out, ref):
         scale = float(b.abs().max())
         assert float((a - b).abs().max()) <= 1e-4 * scale, (float((a - b).abs().max()), scale)

@@ -49,19 +49,15 @@ CASES = [
     ('P: 456->114 no MMA no split', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 48),
     ('P: 19->19 3x3', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 128),
     ('P: 114->95', 240, 320, 114, 95, 1, 1, 116, 116, 0, 2, False, 1, 128),
-    ('Z: dense', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 0),
-    ('Z: dense poll', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 1024),
-    ('Z: dense neither', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 48),
-    ('Z: dense neither poll', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 48 | 1024),
-    ('Z: dense poll profile', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 128 | 1024),
-    ('Z: 19->19 3x3 -> 20', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 1),
-    ('Z: 19->19 3x3 -> 20 poll', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 1 | 1024),
-    ('Z: 456->114 pad ok', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 1),
-    ('Z: 456->114 pad ok poll', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 1 | 1024),
-    ('Z: 114->95 pad ok', 240, 320, 114, 95, 1, 1, 116, 116, 0, 2, False, 1, 1),
-    ('Z: 114->95 pad ok poll', 240, 320, 114, 95, 1, 1, 116, 116, 0, 2, False, 1, 1 | 1024),
+    ('Q: 3x3 30x40 48->4 relu', 30, 40, 48, 4, 9, 1, 48, 4, 0, 1, False, 1, 1),
+    ('Q: 3x3 30x40 4->48 sigmoid', 30, 40, 4, 48, 9, 1, 4, 48, 0, 4, False, 1, 1),
+    ('Q: 3x3 30x40 48->24', 30, 40, 48, 24, 9, 1, 48, 24, 0, 0, False, 1, 1),
+    ('Q: 3x3 60x80 4->48 sigmoid', 60, 80, 4, 48, 9, 1, 4, 48, 0, 4, False, 1, 1),
+    ('Q: 3x3 30x40 8->48 sigmoid', 30, 40, 8, 48, 9, 1, 8, 48, 0, 4, False, 1, 1),
+    ('Q: 3x3 32x48 4->48 sigmoid', 32, 48, 4, 48, 9, 1, 4, 48, 0, 4, False, 1, 1),
+    ('Q: 1x1 30x40 4->48', 30, 40, 4, 48, 1, 1, 4, 48, 0, 0, False, 1, 1),
 ]
-FN = 'ojdf_conv_tc2_batched' if '--v1' not in sys.argv else 'ojdf_conv_tc_batched'
+FN = 'ojdf_conv_tc_batched'
 
 
 def run_case(idx, timing):
@@ -96,7 +92,7 @@ def run_case(idx, timing):
         t = [x.to(dev), torch.from_numpy(packed).to(dev), sc.to(dev), sh.to(dev), out, res.to(dev) if use_res else None]
         keep.append(t)
         probs.append(ConvProblem(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), out.data_ptr(),
-                                 t[5].data_ptr() if use_res else None, istr, ostr, ocoff, d, cout if use_res else 0))
+                                 t[5].data_ptr() if use_res else None, istr, ostr, ocoff, d, cout if use_res else 0, 0, 0))
         refs.append(y)
         outs.append(out)
     arr = (ConvProblem * nprob)(*probs)
