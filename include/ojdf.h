@@ -164,17 +164,20 @@ int ojdf_conv_nhwc_batched(const ojdf_conv_problem *problems_host, int n_problem
  *   - npad_req: 0 = default channel grouping (<= 128 output channels per CTA), or 16..128 (multiple of 16) to
  *     force narrower groups (more CTAs on small feature maps);
  *   - flags: 1 = the caller owns the pad channels [coff+cout, coff+round_up(cout,4)) of the output rows (they
- *     receive zeros; lets a width that is not a multiple of 4 use the TMA-store epilogue, which also needs
+ *     receive zeros or are left untouched; lets a width that is not a multiple of 4 use the TMA-store epilogue, which also needs
  *     out_coffset % 4 == 0, out_stride % 4 == 0 and a 16-byte aligned out_dev -- otherwise a coalesced plain
  *     store path is taken); experiments: 2 = one M-tile per group, 4 = never use halo boxes, 8 = per-thread
- *     stores, 16..2048 and bits 12-15 = timing probes (see the source). */
+ *     stores, 16..2048 and bits 12-15 = timing probes (see the source), 4096 = never split the K loop;
+ *   - scratch_dev (optional, scratch_bytes): lets the K loop be split over several CTAs when the feature map
+ *     is too small to fill the SMs; partial sums are reduced in a fixed order by a second kernel (deterministic). */
 int ojdf_conv_tc_layout(int cout, int npad_req, int *npad, int *groups);
 size_t ojdf_conv_tc_weight_floats(int cin, int cout, int taps, int npad_req);
 /* w_host: (cout, cin, taps) fp32 as in nn.Conv2d.weight (tap = ky*3 + kx); packed_host:
  * ojdf_conv_tc_weight_floats() floats. */
 int ojdf_conv_tc_pack_weights(const float *w_host, int cin, int cout, int taps, int npad_req, float *packed_host);
 int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
-                         int taps, int act, float slope, float out_mul, int npad_req, int flags, void *stream);
+                         int taps, int act, float slope, float out_mul, int npad_req, int flags, float *scratch_dev,
+                         size_t scratch_bytes, void *stream);
 /* nn.AvgPool2d(3, stride 1, padding 1) of VortexPooling (modules/model.py:114-116), C % 4 == 0. */
 int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int W, int C, float *out_dev, int out_stride,
                        void *stream);

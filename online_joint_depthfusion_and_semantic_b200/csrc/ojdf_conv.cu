@@ -397,6 +397,22 @@ nhwc_to_nchw_kernel(const float *__restrict__ in, int in_stride, int in_coff, in
     }
 }
 
+// Second half of a split-K convolution for other translation units (the tensor-core kernel): per problem
+// out[p, coff+c] = out_mul * act(scale[c] * sum_s partial[s][p][c] + shift[c] (+ residual)), fixed summation order.
+int launch_split_reduce(const SplitReduce *problems, int n, int npix, int cout, int cpad, int splits, int act, float slope,
+                        float out_mul, cudaStream_t s)
+{
+    ConvBatch b;
+    for (int i = 0; i < kMaxBatch; ++i) {
+        const SplitReduce &q = problems[i < n ? i : 0];
+        b.p[i] = ConvProblem{nullptr, nullptr, q.scale, q.shift, q.out, q.residual, q.partial, 0, q.out_stride, q.out_coff, 1,
+                             q.res_stride};
+    }
+    dim3 rgrid((unsigned)(((long long)npix * cout + 255) / 256), n);
+    conv_reduce_kernel<<<rgrid, 256, 0, s>>>(b, npix, cout, cpad, splits, act, slope, out_mul);
+    return launched(1);
+}
+
 }  // namespace ojdf
 
 using namespace ojdf;

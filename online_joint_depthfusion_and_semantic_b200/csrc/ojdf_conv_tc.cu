@@ -36,6 +36,8 @@
 namespace ojdf {
 namespace tc {
 
+using ojdf::SplitReduce;
+
 constexpr int kBK = 32;                  // fp32 channels per K chunk (128 bytes)
 constexpr int kBW = 16, kBH = 8;         // M-tile = 8 rows x 16 columns = 128 pixels
 constexpr int kThreads = 608;              // 19 warps, see the role list above
@@ -61,7 +63,8 @@ struct Params {
     CUtensorMap out_map[kMaxBatch];
     Problem p[kMaxBatch];
     int H, W, cin, cout, taps, act, npad, groups, nkc, tiles_x, tiles_y, nprob;
-    int mt, nacc, hd, src_stages, b_stages, src_bytes, box_bytes, bwid, store_mode, dbg, sub_rows, nsub, a_slots, acol0;
+    int mt, nacc, hd, src_stages, b_stages, src_bytes, box_bytes, bwid, store_mode, dbg, sub_rows, nsub, a_slots, acol0, ksplit, cpad;
+    float *partial[kMaxBatch];          // split-K scratch per problem: [ksplit][H*W][cpad] raw partial sums
     float slope, out_mul;
 };
 
@@ -242,12 +245,16 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[16], float (&o)[16
 }
 
 // One work group: up to MT vertically adjacent M-tiles of one (problem, channel group).
-struct Group { int z, g, col, row, n; };
+struct Group { int z, g, col, row, n, ks, kc0, kc1; };
 __device__ __forceinline__ Group decode(const Params &prm, int s, int end)
 {
     const int tiles = prm.tiles_x * prm.tiles_y;
     Group gr;
-    const int t = s % tiles, zg = s / tiles;
+    const int t = s % tiles, r = s / tiles;
+    gr.ks = r % prm.ksplit;                                    // split-K slice: K chunks [kc0, kc1)
+    const int zg = r / prm.ksplit;
+    gr.kc0 = prm.nkc * gr.ks / prm.ksplit;
+    gr.kc1 = prm.nkc * (gr.ks + 1) / prm.ksplit;
     gr.g = zg % prm.groups;
     gr.z = zg / prm.groups;
     gr.col = t / prm.tiles_y;
@@ -287,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kMaxSrc + 2 * kMaxB + 2 * kAS + 2 + s); };
 
     const int tiles = prm.tiles_x * prm.tiles_y;
-    const int total = prm.nprob * prm.groups * tiles;
+    const int total = prm.nprob * prm.groups * prm.ksplit * tiles;
     const int begin = (int)((long long)total * blockIdx.x / gridDim.x);
     const int end = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
     const uint32_t hot_hint = (prm.dbg & 1024) ? 0u : 0x989680u;   // experiment: do not park the A-ring waiters
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const CUtensorMap *map = &prm.in_map[gr.z];
             const int x0 = gr.col * kBW, y0 = gr.row * kBH;
             const uint8_t *wbase = reinterpret_cast<const uint8_t *>(pr.weights) + (size_t)gr.g * prm.taps * prm.nkc * 2u * b_bytes;
-            for (int kc = 0; kc < prm.nkc; ++kc) {
+            for (int kc = gr.kc0; kc < gr.kc1; ++kc) {
                 for (int box = 0; box < nbox; ++box) {
                     const int slot = src_i % HS;
                     if (src_i >= HS) mbar_wait_p(src_empty(slot), ((src_i / HS) - 1) & 1, 0, prof);
@@ -364,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int buf = gc % NACC;
             if (gc >= NACC) mbar_wait_p(acc_empty(buf), ((gc / NACC) - 1) & 1, 3, prof);
             tc_fence_after();
-            for (int kc = 0; kc < prm.nkc; ++kc) {
+            for (int kc = gr.kc0; kc < gr.kc1; ++kc) {
                 for (int tap = 0; tap < prm.taps; ++tap) {
                     const int bs = b_i % BS;
                     mbar_wait_p(b_full(bs), (b_i / BS) & 1, 4, prof);
@@ -377,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         if (!(prm.dbg & 512)) tc_fence_after();
                         const uint32_t acc = tmem + (uint32_t)((buf * MT + mt) * npad);
                         const uint32_t a_hi = tmem + (uint32_t)(prm.acol0 + as * 64), a_lo = a_hi + 32;
-                        const uint32_t first = (uint32_t)(kc | tap);
+                        const uint32_t first = (uint32_t)((kc - gr.kc0) | tap);
                         if (elect_one()) {
                             if (!(prm.dbg & 16)) {
                                 if (prm.dbg & 64) {                          // timing experiment: 1xTF32
@@ -416,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int s = begin; s < end;) {
             const Group gr = decode(prm, s, end);
             const int dil = prm.p[gr.z].dil;
-            for (int kc = 0; kc < prm.nkc; ++kc) {
+            for (int kc = gr.kc0; kc < gr.kc1; ++kc) {
                 for (int box = 0; box < nbox; ++box) {
                     const int slot = src_i % HS;
                     mbar_wait_p(src_full(slot), (src_i / HS) & 1, 7 + 3 * set, prof);
@@ -478,11 +485,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 named_bar(1, kEpiThreads);
                 if (et < npad) {
                     const int co = co_base + et;
-                    s_ss[et] = co < prm.cout ? make_float2(__ldg(pr.scale + co), __ldg(pr.shift + co)) : make_float2(0.f, 0.f);
+                    s_ss[et] = prm.ksplit > 1 ? make_float2(1.f, 0.f)        // split-K: raw partial sums
+                               : co < prm.cout ? make_float2(__ldg(pr.scale + co), __ldg(pr.shift + co)) : make_float2(0.f, 0.f);
                 }
                 named_bar(1, kEpiThreads);
                 cur_zg = gr.z * prm.groups + gr.g;
             }
+            // split-K: pr.out is the problem's scratch, one [H*W][cpad] slab per K slice
+            float *obase = pr.out + (prm.ksplit > 1 ? (size_t)gr.ks * prm.H * prm.W * prm.cpad : (size_t)0);
             mbar_wait_p(acc_full(buf), (gc / NACC) & 1, 13, prof);
             tc_fence_after();
             for (int mt = 0; mt < gr.n; ++mt) {
@@ -507,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     }
                     if (prm.store_mode == 2) {
                         if (live) {
-                            float *orow = pr.out + pix * pr.out_stride + pr.out_coff + co_base;
+                            float *orow = obase + pix * pr.out_stride + pr.out_coff + co_base;
 #pragma unroll
                             for (int c = 0; c < 16; ++c)
                                 if (co_base + n0 + c < prm.cout) orow[n0 + c] = o[c];
@@ -546,14 +556,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                             const int px = gr.col * kBW + rr % kBW, py = (gr.row + mt) * kBH + rr / kBW;
                             if (c < nco && py < prm.H && px < prm.W) {
                                 const float v = *reinterpret_cast<const float *>(stg_ptr + (size_t)rr * 128 + (((c >> 2) ^ (rr & 7)) << 4) + ((c & 3) << 2));
-                                pr.out[((size_t)py * prm.W + px) * pr.out_stride + pr.out_coff + co_base + c] = v;
+                                obase[((size_t)py * prm.W + px) * pr.out_stride + pr.out_coff + co_base + c] = v;
                             }
                         }
                     } else {
                         for (int rr = rbeg; rr < rend; ++rr) {
                             const int px = gr.col * kBW + rr % kBW, py = (gr.row + mt) * kBH + rr / kBW;
                             if (py >= prm.H || px >= prm.W) continue;
-                            float *orow = pr.out + ((size_t)py * prm.W + px) * pr.out_stride + pr.out_coff + co_base;
+                            float *orow = obase + ((size_t)py * prm.W + px) * pr.out_stride + pr.out_coff + co_base;
                             for (int c = lane; c < nco; c += 32)
                                 orow[c] = *reinterpret_cast<const float *>(stg_ptr + (size_t)(c >> 5) * kSlabBytes + (size_t)rr * 128 +
                                                                            ((((c & 31) >> 2) ^ (rr & 7)) << 4) + ((c & 3) << 2));
@@ -740,7 +750,8 @@ extern "C" int ojdf_conv_tc_profile(long long *out_host32)
 }
 
 extern "C" int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H,
-                                    int W, int taps, int act, float slope, float out_mul, int npad_req, int flags, void *stream)
+                                    int W, int taps, int act, float slope, float out_mul, int npad_req, int flags,
+                                    float *scratch_dev, size_t scratch_bytes, void *stream)
 {
     if (!problems_host || n_problems < 1 || n_problems > tc::kMaxBatch || cin < 1 || cout < 1 || H < 1 || W < 1 ||
         H > 32767 || W > 32767 || (taps != 1 && taps != 9) || act < 0 || act > 4)
@@ -849,9 +860,44 @@ extern "C" int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int 
         cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
         attr = true;
     }
-    const long long total = (long long)n_problems * groups * prm.tiles_x * prm.tiles_y;
+    // Split the K loop over several CTAs when the pixels alone cannot fill the SMs (AdapNet++'s 15x20 maps with
+    // 256..2048 input channels): raw partial sums go to the caller's scratch, launch_split_reduce() finishes the layer.
+    const long long items = (long long)n_problems * groups * prm.tiles_x * prm.tiles_y;
+    prm.ksplit = 1;
+    prm.cpad = groups * npad;
+    if (scratch_dev && !(flags & 4096) && items * 2 <= tc::sm_count() && prm.nkc >= 8) {
+        int ks = (int)((tc::sm_count() + items - 1) / items);
+        if (ks > prm.nkc / 4) ks = prm.nkc / 4;                   // at least 4 K chunks per slice
+        if (ks > 16) ks = 16;
+        const size_t per_split = (size_t)n_problems * H * W * prm.cpad * sizeof(float);
+        if ((size_t)ks * per_split > scratch_bytes) ks = (int)(scratch_bytes / per_split);
+        if (ks >= 2) prm.ksplit = ks;
+    }
+    tc::SplitReduce red[tc::kMaxBatch];
+    if (prm.ksplit > 1) {
+        for (int i = 0; i < n_problems; ++i) {
+            const ojdf_conv_problem &q = problems_host[i];
+            float *part = scratch_dev + (size_t)i * prm.ksplit * H * W * prm.cpad;
+            red[i] = tc::SplitReduce{q.scale_dev, q.shift_dev, q.residual_dev, q.out_dev, part, q.out_stride, q.out_coffset,
+                                     q.residual_stride};
+            prm.p[i].out = part;
+            prm.p[i].residual = nullptr;
+            prm.p[i].out_stride = prm.cpad;
+            prm.p[i].out_coff = 0;
+        }
+        prm.cout = prm.cpad;                                     // every accumulator column is stored
+        prm.act = 0;
+        prm.out_mul = 1.0f;
+        prm.store_mode = 1;
+    }
+    const long long total = items * prm.ksplit;
     int grid = tc::sm_count();
     if (grid > total) grid = (int)total;
     tc::conv_tc_kernel<<<grid, tc::kThreads, smem, (cudaStream_t)stream>>>(prm);
+    if (prm.ksplit > 1) {
+        const int r = launched(1);
+        if (r) return r;
+        return launch_split_reduce(red, n_problems, H * W, cout, prm.cpad, prm.ksplit, act, slope, out_mul, (cudaStream_t)stream);
+    }
     return launched(1);
 }

@@ -35,12 +35,10 @@ _TAIL_PIXELS = 300          # 15 x 20: four 128-pixel M-tiles per problem
 
 
 def _npad_for(cout, n_problems, n_tiles=4):
-    """Output-channel group width of the tensor-core kernel on the small tail maps: the widest of
-    128 / 64 / 32 that still yields ~one CTA per SM (tiles x groups x problems >= 120)."""
-    for npad in (128, 64, 32):
-        if n_tiles * n_problems * ((cout + npad - 1) // npad) >= 120:
-            return npad
-    return 32
+    """Output-channel group width of the tensor-core kernel.  The default grouping (<= 128 channels per CTA)
+    is right everywhere now that small maps split their K loop over CTAs (scratch argument); narrower
+    groups only re-read and re-split the same activations."""
+    return 0
 
 
 def _Conv(conv, bn, act, device, n_problems=2, n_tiles=4, **kw):
@@ -169,7 +167,8 @@ class EncoderTailEngine:
             if kind == 'conv':
                 _, arr, n, cin, cout, taps, act, slope, npad_req = step
                 if self.tc:
-                    _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 0, st))
+                    _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 0,
+                                                      self.scratch.data_ptr(), self.scratch.numel() * 4, st))
                 else:
                     _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0,
                                                         self.scratch.data_ptr(), self.scratch.numel() * 4, st))
@@ -375,7 +374,8 @@ class AdapNetEngine:
                 kind = step[0]
                 if kind == 'conv':
                     _, arr, n, cin, cout, H, W, taps, act, slope, npad_req = step
-                    _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 1, st))
+                    _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 1,
+                                                      self.tail.scratch.data_ptr(), self.tail.scratch.numel() * 4, st))
                 elif kind == 'tail':
                     self.tail.run(st)
                 elif kind == 'dropout':

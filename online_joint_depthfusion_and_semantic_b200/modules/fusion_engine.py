@@ -270,7 +270,7 @@ class FusionNetEngine:
                     _, arr, n, cin, cout, taps, act, slope = step[:8]
                     out_mul = step[8] if len(step) > 8 else 1.0
                     if self.tc:
-                        _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, 0, 1, st))   # 1: pads are ours
+                        _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, 0, 1, None, 0, st))   # 1: pads are ours
                     else:
                         _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, None, 0, st))
                 elif kind == 'pool':

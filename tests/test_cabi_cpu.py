@@ -107,4 +107,4 @@ def test_conv_tc_weight_packing_layout(L):
             assert img[g, t, kc, 0, r, chunk, k & 3] == hi[co, ci, t]
             assert img[g, t, kc, 1, r, chunk, k & 3] == lo[co, ci, t]
         assert np.count_nonzero(packed) <= 2 * w.size and not np.isnan(packed).any()
-    assert L.ojdf_conv_tc_batched(None, 1, 32, 32, 8, 16, 1, 0, 0.0, 1.0, 0, 0, None) == -1
+    assert L.ojdf_conv_tc_batched(None, 1, 32, 32, 8, 16, 1, 0, 0.0, 1.0, 0, 0, None, 0, None) == -1

@@ -35,6 +35,8 @@ CASES = [
     ('1x1 15x20 1024 -> 256 narrow groups of 32', 15, 20, 1024, 256, 1, 1, 1024, 512, 0, 1, False, 2, 32, 0),
     ('3x3 240x320 dense block, many groups per CTA', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 0, 1),
     ('1x1 one M-tile per group (flag 2)', 48, 64, 95, 19, 1, 1, 116, 116, 95, 2, False, 2, 0, 2),
+    ('3x3 15x20 512 -> 256 mixed dilations, residual, split K', 15, 20, 512, 256, 9, 4, 512, 256, 0, 1, True, 4, 0, 0),
+    ('3x3 15x20 512 -> 512 without the K split (flag 4096)', 15, 20, 512, 512, 9, 1, 512, 512, 0, 1, False, 1, 0, 4096),
 ]
 
 
@@ -67,8 +69,9 @@ def _run(case):
         refs.append(y)
         outs.append(out)
     arr = (ConvProblem * nprob)(*probs)
-    _lib.check(L.ojdf_conv_tc_batched(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, npad_req, flags,
-                                      torch.cuda.current_stream().cuda_stream))
+    scratch = torch.empty((32 << 20) // 4, dtype=torch.float32, device=DEV)     # lets small maps split their K loop
+    _lib.check(L.ojdf_conv_tc_batched(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, npad_req, flags, scratch.data_ptr() if scratch is not None else None,
+                                      scratch.numel() * 4 if scratch is not None else 0, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     return refs, [o.cpu().double() for o in outs]
 
@@ -81,11 +84,12 @@ def test_conv_tc_matches_fp64(case):
     for y, o in zip(refs, outs):
         got = o[:, ocoff:ocoff + cout]
         assert float((got - y).abs().max()) <= 5e-5 * float(y.abs().max())
-        # nothing outside the layer's own channels is touched (except the pad channels the caller declared its own,
-        # which receive zeros)
+        # nothing outside the layer's own channels is touched, except the pad channels the caller declared its own:
+        # those receive zeros (TMA-store epilogue) or stay as they were (split-K / plain-store epilogues)
         assert bool((o[:, :ocoff] == 7.0).all()) and bool((o[:, ocoff + cout + pad:] == 7.0).all())
         if pad:
-            assert bool((o[:, ocoff + cout:ocoff + cout + pad] == 0.0).all())
+            p_ = o[:, ocoff + cout:ocoff + cout + pad]
+            assert bool((p_ == 0.0).all()) or bool((p_ == 7.0).all())
 
 
 def test_conv_tc_rejects_bad_arguments():
@@ -94,6 +98,6 @@ def test_conv_tc_rejects_bad_arguments():
     x = torch.zeros(128, 32, device=DEV)
     p = ConvProblem(x.data_ptr() + 4, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), None, 32, 32, 0, 1, 0, 0, 0)
     arr = (ConvProblem * 1)(p)
-    assert L.ojdf_conv_tc_batched(arr, 1, 32, 32, 8, 16, 1, 0, 0.0, 1.0, 0, 0, st) == -1       # misaligned input
-    assert L.ojdf_conv_tc_batched(arr, 1, 32, 32, 8, 16, 4, 0, 0.0, 1.0, 0, 0, st) == -1       # taps not 1 or 9
-    assert L.ojdf_conv_tc_batched(None, 1, 32, 32, 8, 16, 1, 0, 0.0, 1.0, 0, 0, st) == -1
+    assert L.ojdf_conv_tc_batched(arr, 1, 32, 32, 8, 16, 1, 0, 0.0, 1.0, 0, 0, None, 0, st) == -1       # misaligned input
+    assert L.ojdf_conv_tc_batched(arr, 1, 32, 32, 8, 16, 4, 0, 0.0, 1.0, 0, 0, None, 0, st) == -1       # taps not 1 or 9
+    assert L.ojdf_conv_tc_batched(None, 1, 32, 32, 8, 16, 1, 0, 0.0, 1.0, 0, 0, None, 0, st) == -1

@@ -49,13 +49,18 @@ CASES = [
     ('P: 456->114 no MMA no split', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 48),
     ('P: 19->19 3x3', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 128),
     ('P: 114->95', 240, 320, 114, 95, 1, 1, 116, 116, 0, 2, False, 1, 128),
-    ('Q: 3x3 30x40 48->4 relu', 30, 40, 48, 4, 9, 1, 48, 4, 0, 1, False, 1, 1),
-    ('Q: 3x3 30x40 4->48 sigmoid', 30, 40, 4, 48, 9, 1, 4, 48, 0, 4, False, 1, 1),
-    ('Q: 3x3 30x40 48->24', 30, 40, 48, 24, 9, 1, 48, 24, 0, 0, False, 1, 1),
-    ('Q: 3x3 60x80 4->48 sigmoid', 60, 80, 4, 48, 9, 1, 4, 48, 0, 4, False, 1, 1),
-    ('Q: 3x3 30x40 8->48 sigmoid', 30, 40, 8, 48, 9, 1, 8, 48, 0, 4, False, 1, 1),
-    ('Q: 3x3 32x48 4->48 sigmoid', 32, 48, 4, 48, 9, 1, 4, 48, 0, 4, False, 1, 1),
-    ('Q: 1x1 30x40 4->48', 30, 40, 4, 48, 1, 1, 4, 48, 0, 0, False, 1, 1),
+    ('K: 1x1 15x20 1024->256 x2', 15, 20, 1024, 256, 1, 1, 1024, 512, 0, 1, False, 2, 0),
+    ('K: 1x1 15x20 1024->256 x2 no split', 15, 20, 1024, 256, 1, 1, 1024, 512, 0, 1, False, 2, 4096),
+    ('K: 1x1 15x20 1024->256 x2 npad32 no split', 15, 20, 1024, 256, 1, 1, 1024, 512, 0, 1, False, 2, 4096 | (32 << 16)),
+    ('K: 3x3 15x20 512->256 x4 dil 2/4', 15, 20, 512, 256, 9, 4, 512, 512, 0, 1, False, 4, 0),
+    ('K: 3x3 15x20 512->256 x4 no split npad32', 15, 20, 512, 256, 9, 4, 512, 512, 0, 1, False, 4, 4096 | (32 << 16)),
+    ('K: 1x1 15x20 512->2048 x2 residual', 15, 20, 512, 2048, 1, 1, 512, 2048, 0, 1, True, 2, 0),
+    ('K: 1x1 15x20 512->2048 x2 residual npad64 no split', 15, 20, 512, 2048, 1, 1, 512, 2048, 0, 1, True, 2, 4096 | (64 << 16)),
+    ('K: 3x3 60x80 280->256', 60, 80, 280, 256, 9, 1, 280, 256, 0, 1, False, 1, 0),
+    ('K: 3x3 60x80 280->256 npad64', 60, 80, 280, 256, 9, 1, 280, 256, 0, 1, False, 1, 64 << 16),
+    ('K: 3x3 60x80 64->64 x2', 60, 80, 64, 64, 9, 1, 64, 64, 0, 1, False, 2, 0),
+    ('K: 1x1 60x80 256->64 x2', 60, 80, 256, 64, 1, 1, 256, 64, 0, 1, False, 2, 0),
+    ('K: 1x1 60x80 64->256 x2 residual', 60, 80, 64, 256, 1, 1, 64, 256, 0, 1, True, 2, 0),
 ]
 FN = 'ojdf_conv_tc_batched'
 
@@ -97,7 +102,9 @@ def run_case(idx, timing):
         outs.append(out)
     arr = (ConvProblem * nprob)(*probs)
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0xffff, st))
+    scratch = torch.empty((64 << 20) // 4, dtype=torch.float32, device=dev)
+    scratch_ptr, scratch_bytes = scratch.data_ptr(), scratch.numel() * 4
+    _lib.check(getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0xffff, scratch_ptr, scratch_bytes, st))
     torch.cuda.synchronize()
     worst = 0.0
     for y, out in zip(refs, outs):
@@ -112,10 +119,10 @@ def run_case(idx, timing):
     if timing:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(3):
-            getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0xffff, st)
+            getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0xffff, scratch_ptr, scratch_bytes, st)
         a.record()
         for _ in range(20):
-            getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0xffff, st)
+            getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0xffff, scratch_ptr, scratch_bytes, st)
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 20
@@ -125,7 +132,7 @@ def run_case(idx, timing):
         prof = (C.c_longlong * 32)()
         L.ojdf_conv_tc_profile.argtypes = [C.c_void_p]
         L.ojdf_conv_tc_profile(prof)                        # discard what the earlier launches accumulated
-        getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0xffff, st)
+        getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0xffff, scratch_ptr, scratch_bytes, st)
         torch.cuda.synchronize()
         L.ojdf_conv_tc_profile(prof)
         p = list(prof)
