@@ -267,11 +267,26 @@ channel_sum4_kernel(const float *__restrict__ in, int in_stride, int npix, int C
     const int per = (npix + gridDim.x - 1) / gridDim.x;
     const int p0 = blockIdx.x * per, p1 = min(p0 + per, npix);
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < lanes)
-        for (int p = p0 + lane; p < p1; p += lanes) {
+    if (lane < lanes) {
+        float4 b = a, c = a, d = a;                            // four independent chains: loads stay in flight
+        int p = p0 + lane;
+        for (; p + 3 * lanes < p1; p += 4 * lanes) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(in + (size_t)p * in_stride) + c4);
+            const float4 v1 = __ldg(reinterpret_cast<const float4 *>(in + (size_t)(p + lanes) * in_stride) + c4);
+            const float4 v2 = __ldg(reinterpret_cast<const float4 *>(in + (size_t)(p + 2 * lanes) * in_stride) + c4);
+            const float4 v3 = __ldg(reinterpret_cast<const float4 *>(in + (size_t)(p + 3 * lanes) * in_stride) + c4);
+            a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+            b.x += v1.x; b.y += v1.y; b.z += v1.z; b.w += v1.w;
+            c.x += v2.x; c.y += v2.y; c.z += v2.z; c.w += v2.w;
+            d.x += v3.x; d.y += v3.y; d.z += v3.z; d.w += v3.w;
+        }
+        for (; p < p1; p += lanes) {
             const float4 v = __ldg(reinterpret_cast<const float4 *>(in + (size_t)p * in_stride) + c4);
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
+        a.x = (a.x + b.x) + (c.x + d.x); a.y = (a.y + b.y) + (c.y + d.y);
+        a.z = (a.z + b.z) + (c.z + d.z); a.w = (a.w + b.w) + (c.w + d.w);
+    }
     s_acc[threadIdx.x] = a;
     __syncthreads();
     if (lane == 0) {
@@ -530,7 +545,12 @@ extern "C" int ojdf_gap_bias(const float *in_dev, int in_stride, int npix, int C
         partial_blocks < 1)
         return OJDF_ERR_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
-    const int pb = partial_blocks < npix ? partial_blocks : npix;
+    // few, fat partial blocks: the second stage (one block) walks them serially per channel
+    int pb = npix / 128;
+    if (pb < 8) pb = 8;
+    if (pb > 64) pb = 64;
+    if (pb > partial_blocks) pb = partial_blocks;
+    if (pb > npix) pb = npix;
     if (!(C & 3) && C <= 1024 && !(in_stride & 3) && !((uintptr_t)in_dev & 15))
         channel_sum4_kernel<<<pb, 256, 0, s>>>(in_dev, in_stride, npix, C, partial_dev);
     else

@@ -336,6 +336,9 @@ class AdapNetEngine:
             self.skip2, self.skip1, self.X16 = self.SK2, self.SK1, self.FX
         # ---- decoder: transposed convolutions / aux heads stay on the library, on channels-last views
         self.J1, self.J2 = z(N8, 280), z(N4, 280)
+        self.dc1 = self._fold_deconv(d.deconv1, d.deconv1_bn)
+        self.dc2 = self._fold_deconv(d.stage2[6], d.stage2[7])
+        self.dc3 = self._fold_deconv(d.stage3[8], d.stage3[9])
         plan.append(('deconv1',))
         s2a, s2b = mk(d.stage2[0], d.stage2[1], 'relu', H8, W8, 1), mk(d.stage2[3], d.stage2[4], 'relu', H8, W8, 1)
         self.U1, self.U2 = z(N8, 256), z(N8, 256)
@@ -351,6 +354,15 @@ class AdapNetEngine:
         conv_step([(s3b, s3b.problem(self.V1, 256, self.V2, 256))], H4, W4)
         conv_step([(s3c, s3c.problem(self.V2, 256, self.V3, Cp))], H4, W4)
         plan.append(('deconv3',))
+
+    @staticmethod
+    def _fold_deconv(deconv, bn):
+        """ConvTranspose2d + BatchNorm2d(eval) -> (weight, bias) of one transposed convolution (folded in f64)."""
+        s = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        w = deconv.weight.detach().double() * s.view(1, -1, 1, 1)          # (cin, cout, kh, kw)
+        b = (deconv.bias.detach().double() if deconv.bias is not None else 0.0) - bn.running_mean.detach().double()
+        b = b * s + bn.bias.detach().double()
+        return w.float().contiguous(), b.float().contiguous()
 
     @staticmethod
     def _nchw(buf, H, W, c0=0, c1=None):
@@ -384,16 +396,16 @@ class AdapNetEngine:
                 elif kind == 'mul':
                     step[1].mul_(step[2])                        # gate * concatenated features (modules/adapnet.py:352)
                 elif kind == 'deconv1':
-                    x = torch.relu(d.deconv1_bn(d.deconv1(self._nchw(self.X16, H16, W16))))
+                    x = torch.relu(F.conv_transpose2d(self._nchw(self.X16, H16, W16), self.dc1[0], self.dc1[1], stride=2, padding=1))
                     aux['y1'] = d._aux(x, d.aux_conv1, d.aux_conv1_bn, 8)
                     self._join(x, self.skip1, d.fuse_conv1, self.J1, H8, W8)
                 elif kind == 'deconv2':
-                    x = d.stage2[7](d.stage2[6](self._nchw(self.U2, H8, W8)))
+                    x = F.conv_transpose2d(self._nchw(self.U2, H8, W8), self.dc2[0], self.dc2[1], stride=2, padding=1)
                     aux['y2'] = d._aux(x, d.aux_conv2, d.aux_conv2_bn, 4)
                     self._join(x, self.skip2, d.fuse_conv2, self.J2, H4, W4)
                 else:                                            # deconv3: x4 transposed convolution + BN on the logits
                     C = int(d.n_classes)
-                    res = d.stage3[9](d.stage3[8](self._nchw(self.V3, H4, W4, 0, C)))
+                    res = F.conv_transpose2d(self._nchw(self.V3, H4, W4, 0, C), self.dc3[0], self.dc3[1], stride=4, padding=2)
         return [res, aux['y1'], aux['y2']]
 
     def _join(self, x, skip, conv, J, H, W):
