@@ -244,6 +244,18 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[16], float (&o)[16
     }
 }
 
+// Position in a ring of `n` stages plus the parity of the current lap (no runtime division in the hot loops).
+// A consumer waits full(idx) with `phase`; a producer waits empty(idx) with `phase ^ 1`, which falls through
+// on the first lap because a fresh mbarrier reports its preceding phase as complete.
+struct Ring {
+    int idx, phase, n;
+    __device__ __forceinline__ explicit Ring(int n_) : idx(0), phase(0), n(n_) {}
+    __device__ __forceinline__ void next()
+    {
+        if (++idx == n) { idx = 0; phase ^= 1; }
+    }
+};
+
 // One work group: up to MT vertically adjacent M-tiles of one (problem, channel group).
 struct Group { int z, g, col, row, n, ks, kc0, kc1; };
 __device__ __forceinline__ Group decode(const Params &prm, int s, int end)
@@ -323,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (whole warp walks the loop, one
         // elected lane issues: keeps addresses and barrier numbers in uniform registers)
-        int src_i = 0, b_i = 0;
+        Ring rs(HS), rb(BS);
         for (int s = begin; s < end;) {
             const Group gr = decode(prm, s, end);
             const Problem &pr = prm.p[gr.z];
@@ -332,8 +344,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint8_t *wbase = reinterpret_cast<const uint8_t *>(pr.weights) + (size_t)gr.g * prm.taps * prm.nkc * 2u * b_bytes;
             for (int kc = gr.kc0; kc < gr.kc1; ++kc) {
                 for (int box = 0; box < nbox; ++box) {
-                    const int slot = src_i % HS;
-                    if (src_i >= HS) mbar_wait_p(src_empty(slot), ((src_i / HS) - 1) & 1, 0, prof);
+                    const int slot = rs.idx;
+                    mbar_wait_p(src_empty(slot), rs.phase ^ 1, 0, prof);
                     int cx = x0 - prm.hd, cy = y0 - prm.hd;
                     if (!halo_mode) { cx = x0 + (box % 3 - 1) * pr.dil; cy = y0 + (box / 3 - 1) * pr.dil; }
                     if (elect_one()) {
@@ -343,18 +355,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                         src_full(slot), kc * kBK, cx, cy + i * prm.sub_rows);
                     }
                     __syncwarp();
-                    ++src_i;
+                    rs.next();
                     for (int tb = 0; tb < taps_per_box; ++tb) {
                         const int tap = halo_mode ? tb : box;
-                        const int bs = b_i % BS;
-                        if (b_i >= BS) mbar_wait_p(b_empty(bs), ((b_i / BS) - 1) & 1, 1, prof);
+                        const int bs = rb.idx;
+                        mbar_wait_p(b_empty(bs), rb.phase ^ 1, 1, prof);
                         if (elect_one()) {
                             mbar_expect_tx(b_full(bs), 2u * b_bytes);
                             bulk_load(bst0 + (uint32_t)bs * 2u * b_bytes, wbase + (size_t)(tap * prm.nkc + kc) * 2u * b_bytes,
                                       2u * b_bytes, b_full(bs));
                         }
                         __syncwarp();
-                        ++b_i;
+                        rb.next();
                     }
                 }
             }
@@ -365,22 +377,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // warp 1 owns the even M-tiles of every group, warp 18 the odd ones: each accumulator has one issuer
         const int par = warp == 1 ? 0 : 1;
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        int cnt = 0, b_i = 0, gc = 0;                           // cnt: A stages consumed by this issuer
-        for (int s = begin; s < end; ++gc) {
+        Ring ra(prm.a_slots), rb(BS), rc(NACC);                 // ra: the A stages of this issuer
+        for (int s = begin; s < end; rc.next()) {
             const Group gr = decode(prm, s, end);
-            const int buf = gc % NACC;
-            if (gc >= NACC) mbar_wait_p(acc_empty(buf), ((gc / NACC) - 1) & 1, 3, prof);
+            const int buf = rc.idx;
+            mbar_wait_p(acc_empty(buf), rc.phase ^ 1, 3, prof);
             tc_fence_after();
             for (int kc = gr.kc0; kc < gr.kc1; ++kc) {
                 for (int tap = 0; tap < prm.taps; ++tap) {
-                    const int bs = b_i % BS;
-                    mbar_wait_p(b_full(bs), (b_i / BS) & 1, 4, prof);
+                    const int bs = rb.idx;
+                    mbar_wait_p(b_full(bs), rb.phase, 4, prof);
                     const uint32_t sb = bst0 + (uint32_t)bs * 2u * b_bytes;
                     const uint64_t b_hi = smem_desc(sb), b_lo = smem_desc(sb + b_bytes);
-                    for (int mt = par; mt < gr.n; mt += 2, ++cnt) {
-                        // issuer `par` and splitter set `par` form an in-order pipeline over A slots 2*par, 2*par+1
-                        const int as = par * prm.a_slots + cnt % prm.a_slots;
-                        mbar_wait_p(a_full(as), (cnt / prm.a_slots) & 1, 5, prof, hot_hint);
+                    for (int mt = par; mt < gr.n; mt += 2, ra.next()) {
+                        // issuer `par` and splitter set `par` form an in-order pipeline over their own A slots
+                        const int as = par * prm.a_slots + ra.idx;
+                        mbar_wait_p(a_full(as), ra.phase, 5, prof, hot_hint);
                         if (!(prm.dbg & 512)) tc_fence_after();
                         const uint32_t acc = tmem + (uint32_t)((buf * MT + mt) * npad);
                         const uint32_t a_hi = tmem + (uint32_t)(prm.acol0 + as * 64), a_lo = a_hi + 32;
@@ -407,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     }
                     if (elect_one()) umma_commit(b_empty(bs));
                     __syncwarp();
-                    ++b_i;
+                    rb.next();
                 }
             }
             if (elect_one()) umma_commit(acc_full(buf));
@@ -419,22 +431,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int set = (warp - 2) >> 2;
         const int q = warp & 3;
         const int m = q * 32 + lane, ty = m / kBW, tx = m % kBW;
-        int cnt = 0, src_i = 0;                                 // cnt: A stages produced by this set
+        Ring ra(prm.a_slots), rs(HS);                           // ra: the A stages produced by this set
         for (int s = begin; s < end;) {
             const Group gr = decode(prm, s, end);
             const int dil = prm.p[gr.z].dil;
             for (int kc = gr.kc0; kc < gr.kc1; ++kc) {
                 for (int box = 0; box < nbox; ++box) {
-                    const int slot = src_i % HS;
-                    mbar_wait_p(src_full(slot), (src_i / HS) & 1, 7 + 3 * set, prof);
+                    const int slot = rs.idx;
+                    mbar_wait_p(src_full(slot), rs.phase, 7 + 3 * set, prof);
                     const uint8_t *src = smem + (size_t)slot * prm.src_bytes;
                     for (int tb = 0; tb < taps_per_box; ++tb) {
                         int oy = 0, ox = 0;
                         if (halo_mode && prm.taps == 9) { oy = prm.hd + (tb / 3 - 1) * dil; ox = prm.hd + (tb % 3 - 1) * dil; }
-                        for (int mt = set; mt < gr.n; mt += 2, ++cnt) {
-                            const int as = set * prm.a_slots + cnt % prm.a_slots, use = cnt / prm.a_slots;
+                        for (int mt = set; mt < gr.n; mt += 2, ra.next()) {
+                            const int as = set * prm.a_slots + ra.idx;
                             if (prm.dbg & 32) {                                  // timing experiment: no split work
-                                if (use >= 1) mbar_wait(a_empty(as), (use - 1) & 1);
+                                mbar_wait(a_empty(as), ra.phase ^ 1);
                                 mbar_arrive(a_full(as));
                                 continue;
                             }
@@ -452,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                     lo[4 * j + e] = __float_as_uint(__uint_as_float(xs[e]) - __uint_as_float(h));
                                 }
                             }
-                            if (use >= 1) mbar_wait_p(a_empty(as), (use - 1) & 1, 8 + 3 * set, prof, hot_hint);
+                            mbar_wait_p(a_empty(as), ra.phase ^ 1, 8 + 3 * set, prof, hot_hint);
                             tc_fence_after();
                             const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(prm.acol0 + as * 64);
                             tmem_st32(ta, hi);
@@ -463,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         }
                     }
                     mbar_arrive(src_empty(slot));
-                    ++src_i;
+                    rs.next();
                 }
             }
             s += gr.n;
@@ -475,11 +487,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int et = threadIdx.x - kEpi0 * 32;                // 0..255
         const int m = q * 32 + lane, ty = m / kBW, tx = m % kBW;
         const int nslab = (npad + 31) / 32;
-        int gc = 0, cur_zg = -1;
-        for (int s = begin; s < end; ++gc) {
+        int cur_zg = -1;
+        Ring rc(NACC);
+        for (int s = begin; s < end; rc.next()) {
             const Group gr = decode(prm, s, end);
             const Problem &pr = prm.p[gr.z];
-            const int buf = gc % NACC;
+            const int buf = rc.idx;
             const int co_base = gr.g * npad;
             if (cur_zg != gr.z * prm.groups + gr.g) {            // (scale, shift) of this channel group -> smem
                 named_bar(1, kEpiThreads);
@@ -493,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             // split-K: pr.out is the problem's scratch, one [H*W][cpad] slab per K slice
             float *obase = pr.out + (prm.ksplit > 1 ? (size_t)gr.ks * prm.H * prm.W * prm.cpad : (size_t)0);
-            mbar_wait_p(acc_full(buf), (gc / NACC) & 1, 13, prof);
+            mbar_wait_p(acc_full(buf), rc.phase, 13, prof);
             tc_fence_after();
             for (int mt = 0; mt < gr.n; ++mt) {
                 const int x = gr.col * kBW + tx, y = (gr.row + mt) * kBH + ty;

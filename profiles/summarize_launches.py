@@ -22,7 +22,7 @@ def main(path, top=30):
     print('%-90s %6s %10s %9s %6s' % ('kernel', 'n', 'sum_us', 'mean_us', 'share'))
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]))[:top]:
         print('%-90s %6d %10.1f %9.2f %5.1f%%' % (k[:90], len(v), sum(v), sum(v) / len(v), 100 * sum(v) / tot))
-    mine = {k: v for k, v in agg.items() if 'ojdf' in k}
+    mine = {k: v for k, v in agg.items() if 'ojdf' in k or 'conv_tc' in k}
     print('\nown kernels (libojdf.so): %.1f us = %.2f%% of the captured step time' %
           (sum(sum(v) for v in mine.values()), 100 * sum(sum(v) for v in mine.values()) / tot))
     for k, v in mine.items():
