@@ -280,6 +280,7 @@ __device__ __forceinline__ Group decode(const Params &prm, int s, int end)
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ Params prm)
 {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the next layer's prologue start early
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bars[2 * kMaxSrc + 2 * kMaxB + 2 * kAS + 4];
     __shared__ uint32_t s_tmem;
@@ -329,6 +330,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+    // Programmatic dependent launch: everything above (barriers, TMEM) overlapped the tail of the previous
+    // kernel in the stream; from here on this grid reads what that kernel wrote.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const bool prof = (prm.dbg & 128) && blockIdx.x == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6 || warp == kEpi0);
     const long long t_role0 = prof ? clock64() : 0;
 
@@ -906,7 +910,20 @@ extern "C" int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int 
     const long long total = items * prm.ksplit;
     int grid = tc::sm_count();
     if (grid > total) grid = (int)total;
-    tc::conv_tc_kernel<<<grid, tc::kThreads, smem, (cudaStream_t)stream>>>(prm);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(tc::kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = (flags & 8192) ? 0 : 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, tc::conv_tc_kernel, prm);
+        if (le != cudaSuccess) { cudaGetLastError(); return (int)le; }
+    }
     if (prm.ksplit > 1) {
         const int r = launched(1);
         if (r) return r;
