@@ -291,7 +291,7 @@ def run_own(args):
     line = {
         'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64 ray geometry / f32 accumulation / f16+u8 volumes; FusionNet + AdapNet++ 15x20 tail: fp32 via 3xTF32 tcgen05 (own kernels, ~1e-6 of fp32); rest of AdapNet++ f32 library convs (TF32 off)',
+        'dtype': 'f64 ray geometry / f32 accumulation / f16+u8 volumes; FusionNet + AdapNet++ convolutions: fp32 via 3xTF32 tcgen05 (own kernels, ~1e-6 of fp32); AdapNet++ stem / 3 transposed convs: f32 library (TF32 off)',
         'data': 'synthetic (analytic SDF room, seeded; random-init networks seed 1911)',
         'config': {'workload': WORKLOAD, 'frame': [H, W], 'grid': GRID, 'scenes_per_gpu': SCENES_PER_RANK,
                    'sharding': 'scenes one-per-rank, no collective',

@@ -216,6 +216,7 @@ class AdapNet(nn.Module):
     _full_engine = None
     use_engine = True
     whole_engine = True         # False: only the 15x20 tail runs on libojdf, the rest on the library
+    aux_heads = True            # False: the engine returns [res, None, None] (the fusion pipeline reads only res)
 
     def _drop_engines(self):
         self._engine = None

@@ -397,11 +397,11 @@ class AdapNetEngine:
                     step[1].mul_(step[2])                        # gate * concatenated features (modules/adapnet.py:352)
                 elif kind == 'deconv1':
                     x = torch.relu(F.conv_transpose2d(self._nchw(self.X16, H16, W16), self.dc1[0], self.dc1[1], stride=2, padding=1))
-                    aux['y1'] = d._aux(x, d.aux_conv1, d.aux_conv1_bn, 8)
+                    aux['y1'] = d._aux(x, d.aux_conv1, d.aux_conv1_bn, 8) if net.aux_heads else None
                     self._join(x, self.skip1, d.fuse_conv1, self.J1, H8, W8)
                 elif kind == 'deconv2':
                     x = F.conv_transpose2d(self._nchw(self.U2, H8, W8), self.dc2[0], self.dc2[1], stride=2, padding=1)
-                    aux['y2'] = d._aux(x, d.aux_conv2, d.aux_conv2_bn, 4)
+                    aux['y2'] = d._aux(x, d.aux_conv2, d.aux_conv2_bn, 4) if net.aux_heads else None
                     self._join(x, self.skip2, d.fuse_conv2, self.J2, H4, W4)
                 else:                                            # deconv3: x4 transposed convolution + BN on the logits
                     C = int(d.n_classes)

@@ -67,6 +67,7 @@ class Pipeline(nn.Module):
         """image (b,3,h,w) raw batch image, aux (b,h,w)|(b,1,h,w) second modality or None."""
         image = (image / 255.0).float()                                # quirk: /255 after mean/std normalisation
         net = self._semantic_2d_network
+        net.aux_heads = False                                          # only the main head is read below (:54-58)
         if self.config.SEMANTIC_2D_MODEL.stage == 1:
             logits = net(image if aux is None else aux.repeat(1, 3, 1, 1).float())[0]
         else:

@@ -101,3 +101,30 @@ def test_conv_tc_rejects_bad_arguments():
     assert L.ojdf_conv_tc_batched(arr, 1, 32, 32, 8, 16, 1, 0, 0.0, 1.0, 0, 0, None, 0, st) == -1       # misaligned input
     assert L.ojdf_conv_tc_batched(arr, 1, 32, 32, 8, 16, 4, 0, 0.0, 1.0, 0, 0, None, 0, st) == -1       # taps not 1 or 9
     assert L.ojdf_conv_tc_batched(None, 1, 32, 32, 8, 16, 1, 0, 0.0, 1.0, 0, 0, None, 0, st) == -1
+
+
+def test_conv_tc_strided_input_matches_stride2_conv():
+    """in_step = 2: a 1x1 convolution with stride 2 (ResNet down-sampling, torchvision Bottleneck.downsample) and
+    a stride-2 3x3 expressed as the stride-1 3x3 followed by a strided 1x1 read (modules/adapnet_engine.py)."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(9)
+    Hin, Win, cin, cout = 30, 40, 96, 80
+    Ho, Wo = Hin // 2, Win // 2
+    x = torch.randn(Hin * Win, cin, generator=g)
+    w = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    sc, sh = 0.5 + torch.rand(cout, generator=g), 0.1 * torch.randn(cout, generator=g)
+    ref = torch.nn.functional.conv2d(x.double().t().reshape(1, cin, Hin, Win), w.double(), stride=2)[0]
+    ref = (ref.reshape(cout, Ho * Wo).t() * sc.double() + sh.double()).clamp(min=0)
+    packed = np.zeros(L.ojdf_conv_tc_weight_floats(cin, cout, 1, 0), np.float32)
+    wc = np.ascontiguousarray(w.numpy().reshape(cout, cin, 1))
+    _lib.check(L.ojdf_conv_tc_pack_weights(wc.ctypes.data, cin, cout, 1, 0, packed.ctypes.data))
+    xd, pd, scd, shd = x.to(DEV), torch.from_numpy(packed).to(DEV), sc.to(DEV), sh.to(DEV)
+    out = torch.full((Ho * Wo, cout), 7.0, device=DEV)
+    p = ConvProblem(xd.data_ptr(), pd.data_ptr(), scd.data_ptr(), shd.data_ptr(), out.data_ptr(), None, cin, cout, 0, 1, 0, 2, Win)
+    arr = (ConvProblem * 1)(p)
+    _lib.check(L.ojdf_conv_tc_batched(arr, 1, cin, cout, Ho, Wo, 1, 1, 0.0, 1.0, 0, 0, None, 0, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert float((out.cpu().double() - ref).abs().max()) <= 5e-5 * float(ref.abs().max())
+    bad = ConvProblem(xd.data_ptr(), pd.data_ptr(), scd.data_ptr(), shd.data_ptr(), out.data_ptr(), None, cin, cout, 0, 1, 0, 2, Wo)
+    assert L.ojdf_conv_tc_batched((ConvProblem * 1)(bad), 1, cin, cout, Ho, Wo, 1, 1, 0.0, 1.0, 0, 0, None, 0,
+                                  torch.cuda.current_stream().cuda_stream) == -1          # input row narrower than the reads
