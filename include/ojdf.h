@@ -143,6 +143,12 @@ typedef struct ojdf_conv_problem {
     int in_step;                    /* tensor-core kernel only: 0/1 = dense, 2 = read every other input pixel of every
                                      * other row (stride-2 1x1 convolutions, ResNet down-sampling); H, W stay OUTPUT sizes */
     int in_width;                   /* pixels per input row when in_step > 1 (the input image is in_width wide) */
+    int out_step;                   /* tensor-core kernel only: 0/1 = dense, k = output pixel (y, x) of this problem is pixel
+                                     * (k*y, k*x) of an image that is out_width pixels wide, counted from out_dev (one phase of a
+                                     * transposed convolution; needs the TMA-store epilogue) */
+    int out_width;
+    int tap_mask;                   /* 3x3 only: bit t set = tap t (ky*3+kx) contributes; 0 = all nine.  Taps whose shifted
+                                     * window lies entirely outside the image are dropped automatically */
 } ojdf_conv_problem;
 /* act additionally accepts 4 = sigmoid.  scratch_dev (optional, scratch_bytes): when the pixel count
  * alone cannot fill the GPU (AdapNet++'s 15x20 maps) the K loop is split across blocks, partial sums go

@@ -493,7 +493,7 @@ static bool problem_ok(const ojdf_conv_problem &q, int cin, int cout)
 {
     return q.in_dev && q.weights_dev && q.scale_dev && q.shift_dev && q.out_dev && !(q.in_stride & 3) &&
            q.in_stride >= ((cin + 3) & ~3) && q.out_stride >= q.out_coffset + cout && q.out_coffset >= 0 && q.dilation >= 1 &&
-           (!q.residual_dev || q.residual_stride >= cout) && q.in_step <= 1;
+           (!q.residual_dev || q.residual_stride >= cout) && q.in_step <= 1 && q.out_step <= 1;
 }
 
 extern "C" int ojdf_conv_nhwc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H,
@@ -520,7 +520,7 @@ extern "C" int ojdf_conv_nhwc(const float *in_dev, int in_stride, int cin, int H
                               void *stream)
 {
     ojdf_conv_problem q = {in_dev, weights_dev, scale_dev, shift_dev, out_dev, nullptr, in_stride, out_stride, out_coffset,
-                           dilation, 0, 0, 0};
+                           dilation, 0, 0, 0, 0, 0, 0};
     return ojdf_conv_nhwc_batched(&q, 1, cin, cout, H, W, taps, act, slope, out_mul, nullptr, 0, stream);
 }
 

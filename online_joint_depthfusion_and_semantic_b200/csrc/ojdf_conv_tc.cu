@@ -64,6 +64,7 @@ struct Params {
     Problem p[kMaxBatch];
     int H, W, cin, cout, taps, act, npad, groups, nkc, tiles_x, tiles_y, nprob;
     int mt, nacc, hd, src_stages, b_stages, src_bytes, box_bytes, bwid, store_mode, dbg, sub_rows, nsub, a_slots, acol0, ksplit, cpad;
+    int tap_mask[kMaxBatch];            // live taps of each problem (bit t = tap t), never 0
     float *partial[kMaxBatch];          // split-K scratch per problem: [ksplit][H*W][cpad] raw partial sums
     float slope, out_mul;
 };
@@ -346,8 +347,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const CUtensorMap *map = &prm.in_map[gr.z];
             const int x0 = gr.col * kBW, y0 = gr.row * kBH;
             const uint8_t *wbase = reinterpret_cast<const uint8_t *>(pr.weights) + (size_t)gr.g * prm.taps * prm.nkc * 2u * b_bytes;
+            const int mask = prm.tap_mask[gr.z];
             for (int kc = gr.kc0; kc < gr.kc1; ++kc) {
                 for (int box = 0; box < nbox; ++box) {
+                    if (!halo_mode && !((mask >> box) & 1)) continue;        // dead tap: no box, no weights, no MMAs
                     const int slot = rs.idx;
                     mbar_wait_p(src_empty(slot), rs.phase ^ 1, 0, prof);
                     int cx = x0 - prm.hd, cy = y0 - prm.hd;
@@ -362,6 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     rs.next();
                     for (int tb = 0; tb < taps_per_box; ++tb) {
                         const int tap = halo_mode ? tb : box;
+                        if (!((mask >> tap) & 1)) continue;
                         const int bs = rb.idx;
                         mbar_wait_p(b_empty(bs), rb.phase ^ 1, 1, prof);
                         if (elect_one()) {
@@ -387,8 +391,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int buf = rc.idx;
             mbar_wait_p(acc_empty(buf), rc.phase ^ 1, 3, prof);
             tc_fence_after();
+            const int mask = prm.tap_mask[gr.z], tap0 = __ffs(mask) - 1;
             for (int kc = gr.kc0; kc < gr.kc1; ++kc) {
                 for (int tap = 0; tap < prm.taps; ++tap) {
+                    if (!((mask >> tap) & 1)) continue;
                     const int bs = rb.idx;
                     mbar_wait_p(b_full(bs), rb.phase, 4, prof);
                     const uint32_t sb = bst0 + (uint32_t)bs * 2u * b_bytes;
@@ -400,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         if (!(prm.dbg & 512)) tc_fence_after();
                         const uint32_t acc = tmem + (uint32_t)((buf * MT + mt) * npad);
                         const uint32_t a_hi = tmem + (uint32_t)(prm.acol0 + as * 64), a_lo = a_hi + 32;
-                        const uint32_t first = (uint32_t)((kc - gr.kc0) | tap);
+                        const uint32_t first = (uint32_t)((kc - gr.kc0) | (tap ^ tap0));   // 0 only for the group's first K step
                         if (elect_one()) {
                             if (!(prm.dbg & 16)) {
                                 if (prm.dbg & 64) {                          // timing experiment: 1xTF32
@@ -439,12 +445,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int s = begin; s < end;) {
             const Group gr = decode(prm, s, end);
             const int dil = prm.p[gr.z].dil;
+            const int mask = prm.tap_mask[gr.z];
             for (int kc = gr.kc0; kc < gr.kc1; ++kc) {
                 for (int box = 0; box < nbox; ++box) {
+                    if (!halo_mode && !((mask >> box) & 1)) continue;
                     const int slot = rs.idx;
                     mbar_wait_p(src_full(slot), rs.phase, 7 + 3 * set, prof);
                     const uint8_t *src = smem + (size_t)slot * prm.src_bytes;
                     for (int tb = 0; tb < taps_per_box; ++tb) {
+                        if (!((mask >> (halo_mode ? tb : box)) & 1)) continue;
                         int oy = 0, ox = 0;
                         if (halo_mode && prm.taps == 9) { oy = prm.hd + (tb / 3 - 1) * dil; ox = prm.hd + (tb % 3 - 1) * dil; }
                         for (int mt = set; mt < gr.n; mt += 2, ra.next()) {
@@ -864,10 +873,20 @@ extern "C" int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int 
         int r = tc::pixel_map(q.in_dev, cin, q.in_stride * step, H, W, prm.bwid, prm.sub_rows, &prm.in_map[i],
                               step > 1 ? (long long)q.in_stride * q.in_width * step : 0);
         if (r) return r;
+        const int ostep = q.out_step > 1 ? q.out_step : 1;
+        if (ostep > 1 && (prm.store_mode != 0 || q.out_width < (W - 1) * ostep + 1)) return OJDF_ERR_BADARG;
         if (prm.store_mode == 0) {
-            r = tc::pixel_map(q.out_dev, q.out_coffset + ((cout + 3) & ~3), q.out_stride, H, W, tc::kBW, tc::kBH, &prm.out_map[i]);
+            r = tc::pixel_map(q.out_dev, q.out_coffset + ((cout + 3) & ~3), q.out_stride * ostep, H, W, tc::kBW, tc::kBH,
+                              &prm.out_map[i], ostep > 1 ? (long long)q.out_stride * q.out_width * ostep : 0);
             if (r) return r;
         }
+        int mask = taps == 9 ? (q.tap_mask ? (q.tap_mask & 511) : 511) : 1;
+        if (taps == 9) {                                         // taps that only ever see the zero padding
+            for (int t = 0; t < 9; ++t)
+                if (abs(t / 3 - 1) * q.dilation >= H || abs(t % 3 - 1) * q.dilation >= W) mask &= ~(1 << t);
+            if (!mask) mask = 1 << 4;
+        }
+        prm.tap_mask[i] = mask;
         prm.p[i] = tc::Problem{q.weights_dev, q.scale_dev, q.shift_dev, q.out_dev, q.residual_dev,
                                 q.out_stride, q.out_coffset, q.dilation, q.residual_stride};
     }
@@ -882,7 +901,9 @@ extern "C" int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int 
     const long long items = (long long)n_problems * groups * prm.tiles_x * prm.tiles_y;
     prm.ksplit = 1;
     prm.cpad = groups * npad;
-    if (scratch_dev && !(flags & 4096) && items * 2 <= tc::sm_count() && prm.nkc >= 8) {
+    bool strided_out = false;
+    for (int i = 0; i < n_problems; ++i) strided_out = strided_out || problems_host[i].out_step > 1;
+    if (scratch_dev && !(flags & 4096) && !strided_out && items * 2 <= tc::sm_count() && prm.nkc >= 8) {
         int ks = (int)((tc::sm_count() + items - 1) / items);
         if (ks > prm.nkc / 4) ks = prm.nkc / 4;                   // at least 4 K chunks per slice
         if (ks > 16) ks = 16;

@@ -1,9 +1,10 @@
 """Inference engines for AdapNet++ on libojdf's tap-GEMM kernels.
 
 `AdapNetEngine` (bottom of this file) runs the whole network pixel-major: everything except the 7x7 stem,
-the max-pool, the three transposed convolutions and the bilinear aux heads is a fused conv + BatchNorm +
-activation (+ residual) launch of the tensor-core kernel (csrc/ojdf_conv_tc.cu); stride-2 layers are the
-stride-1 layer followed by a consumer that reads every other pixel (`in_step = 2`).  It embeds
+the max-pool and the (optional) bilinear aux heads is a fused conv + BatchNorm + activation (+ residual)
+launch of the tensor-core kernel (csrc/ojdf_conv_tc.cu); stride-2 layers are the stride-1 layer followed by a
+consumer that reads every other pixel (`in_step = 2`); the three transposed convolutions are 4 / 16 phase
+convolutions that write every 2nd / 4th output pixel (`out_step`, dead taps masked).  It embeds
 `EncoderTailEngine`, described next.
 
 Low-resolution tail:
@@ -326,6 +327,36 @@ class AdapNetEngine:
             conv_step([(fin, fin.problem(GATE, 2 * feat, out, feat))], H, W)
             return out
 
+        def deconv(m, bn, act, src, src_stride, Hin, Win, dst, dst_stride):
+            """ConvTranspose2d(k = 2s, stride s, padding s/2) + BatchNorm (+ act) as s*s phase convolutions:
+            output pixel (s*y + a, s*x + b) = 3x3 window of the input around (y, x) with the kernel taps
+            ky = a + p - s*dy, kx = b + p - s*dx that exist (4 of the 9); each phase is one problem of the
+            tensor-core kernel writing every s-th pixel of the output (out_step), dead taps masked."""
+            sdc, k, pad = int(m.stride[0]), int(m.kernel_size[0]), int(m.padding[0])
+            assert k == 2 * sdc and 2 * pad == sdc and int(m.output_padding[0]) == 0
+            Wt = m.weight.detach().cpu()                                  # (cin, cout, k, k)
+            cin, cout = Wt.shape[:2]
+            Wout = Win * sdc
+            pairs = []
+            for a in range(sdc):
+                for b in range(sdc):
+                    fake = torch.nn.Conv2d(cin, cout, 3, padding=1, bias=True)
+                    wp, mask = torch.zeros(cout, cin, 3, 3), 0
+                    for dy in (-1, 0, 1):
+                        ky = a + pad - sdc * dy
+                        for dx in (-1, 0, 1):
+                            kx = b + pad - sdc * dx
+                            if 0 <= ky < k and 0 <= kx < k:
+                                wp[:, :, dy + 1, dx + 1] = Wt[:, :, ky, kx].t()
+                                mask |= 1 << ((dy + 1) * 3 + dx + 1)
+                    fake.weight.data.copy_(wp)
+                    fake.bias.data.copy_(m.bias.detach().cpu() if m.bias is not None else torch.zeros(cout))
+                    c = mk(fake, bn, act, Hin, Win, sdc * sdc)
+                    pairs.append((c, c.problem(src, src_stride, dst, dst_stride, 0, out_step=sdc, out_width=Wout,
+                                               tap_mask=mask, dst_ptr_offset=(a * Wout + b) * dst_stride)))
+            for i in range(0, len(pairs), 8):
+                conv_step(pairs[i:i + 8], Hin, Win)
+
         d = net.decoder
         C = int(d.n_classes)
         if self.stage2:
@@ -336,15 +367,14 @@ class AdapNetEngine:
             self.skip2, self.skip1, self.X16 = self.SK2, self.SK1, self.FX
         # ---- decoder: transposed convolutions / aux heads stay on the library, on channels-last views
         self.J1, self.J2 = z(N8, 280), z(N4, 280)
-        self.dc1 = self._fold_deconv(d.deconv1, d.deconv1_bn)
-        self.dc2 = self._fold_deconv(d.stage2[6], d.stage2[7])
-        self.dc3 = self._fold_deconv(d.stage3[8], d.stage3[9])
-        plan.append(('deconv1',))
+        deconv(d.deconv1, d.deconv1_bn, 'relu', self.X16, 256, H16, W16, self.J1, 280)
+        plan.append(('join1',))
         s2a, s2b = mk(d.stage2[0], d.stage2[1], 'relu', H8, W8, 1), mk(d.stage2[3], d.stage2[4], 'relu', H8, W8, 1)
         self.U1, self.U2 = z(N8, 256), z(N8, 256)
         conv_step([(s2a, s2a.problem(self.J1, 280, self.U1, 256))], H8, W8)
         conv_step([(s2b, s2b.problem(self.U1, 256, self.U2, 256))], H8, W8)
-        plan.append(('deconv2',))
+        deconv(d.stage2[6], d.stage2[7], 'none', self.U2, 256, H8, W8, self.J2, 280)
+        plan.append(('join2',))
         s3a, s3b = mk(d.stage3[0], d.stage3[1], 'relu', H4, W4, 1), mk(d.stage3[3], d.stage3[4], 'relu', H4, W4, 1)
         s3c = mk(d.stage3[6], d.stage3[7], 'none', H4, W4, 1)
         Cp = _pad4(C)
@@ -353,16 +383,8 @@ class AdapNetEngine:
         conv_step([(s3a, s3a.problem(self.J2, 280, self.V1, 256))], H4, W4)
         conv_step([(s3b, s3b.problem(self.V1, 256, self.V2, 256))], H4, W4)
         conv_step([(s3c, s3c.problem(self.V2, 256, self.V3, Cp))], H4, W4)
-        plan.append(('deconv3',))
-
-    @staticmethod
-    def _fold_deconv(deconv, bn):
-        """ConvTranspose2d + BatchNorm2d(eval) -> (weight, bias) of one transposed convolution (folded in f64)."""
-        s = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
-        w = deconv.weight.detach().double() * s.view(1, -1, 1, 1)          # (cin, cout, kh, kw)
-        b = (deconv.bias.detach().double() if deconv.bias is not None else 0.0) - bn.running_mean.detach().double()
-        b = b * s + bn.bias.detach().double()
-        return w.float().contiguous(), b.float().contiguous()
+        self.LG = z(h * w, Cp)                                   # logits, pixel-major
+        deconv(d.stage3[8], d.stage3[9], 'none', self.V3, Cp, H4, W4, self.LG, Cp)
 
     @staticmethod
     def _nchw(buf, H, W, c0=0, c1=None):
@@ -395,24 +417,21 @@ class AdapNetEngine:
                         t.copy_(F.dropout(t, p=0.5, training=True))
                 elif kind == 'mul':
                     step[1].mul_(step[2])                        # gate * concatenated features (modules/adapnet.py:352)
-                elif kind == 'deconv1':
-                    x = torch.relu(F.conv_transpose2d(self._nchw(self.X16, H16, W16), self.dc1[0], self.dc1[1], stride=2, padding=1))
+                elif kind == 'join1':
+                    x = self._nchw(self.J1, H8, W8, 0, 256)      # relu(bn(deconv1(.))), written by the phase convolutions
                     aux['y1'] = d._aux(x, d.aux_conv1, d.aux_conv1_bn, 8) if net.aux_heads else None
                     self._join(x, self.skip1, d.fuse_conv1, self.J1, H8, W8)
-                elif kind == 'deconv2':
-                    x = F.conv_transpose2d(self._nchw(self.U2, H8, W8), self.dc2[0], self.dc2[1], stride=2, padding=1)
+                else:                                            # join2
+                    x = self._nchw(self.J2, H4, W4, 0, 256)
                     aux['y2'] = d._aux(x, d.aux_conv2, d.aux_conv2_bn, 4) if net.aux_heads else None
                     self._join(x, self.skip2, d.fuse_conv2, self.J2, H4, W4)
-                else:                                            # deconv3: x4 transposed convolution + BN on the logits
-                    C = int(d.n_classes)
-                    res = F.conv_transpose2d(self._nchw(self.V3, H4, W4, 0, C), self.dc3[0], self.dc3[1], stride=4, padding=2)
+            res = self._nchw(self.LG, self.h, self.w, 0, int(d.n_classes))     # (1, C, h, w) view of the pixel-major logits
         return [res, aux['y1'], aux['y2']]
 
     def _join(self, x, skip, conv, J, H, W):
         """Decoder._join (modules/adapnet.py:305-315): [x | gate * skip] into the 280-channel buffer J."""
         d = self.net.decoder
-        Jv = J.view(1, H, W, 280)
-        Jv[..., :256].copy_(x.permute(0, 2, 3, 1))
+        Jv = J.view(1, H, W, 280)                               # channels [0, 256) already hold x
         sk = skip.view(1, H, W, 24)
         if d.fusion:
             gate = torch.relu(conv(F.adaptive_avg_pool2d(x, 1))).reshape(1, 1, 1, 24)

@@ -64,7 +64,7 @@ class ConvProblem(C.Structure):
     _fields_ = [('in_dev', C.c_void_p), ('weights_dev', C.c_void_p), ('scale_dev', C.c_void_p), ('shift_dev', C.c_void_p),
                 ('out_dev', C.c_void_p), ('residual_dev', C.c_void_p), ('in_stride', C.c_int), ('out_stride', C.c_int),
                 ('out_coffset', C.c_int), ('dilation', C.c_int), ('residual_stride', C.c_int), ('in_step', C.c_int),
-                ('in_width', C.c_int)]
+                ('in_width', C.c_int), ('out_step', C.c_int), ('out_width', C.c_int), ('tap_mask', C.c_int)]
 
 
 class _Conv:
@@ -105,12 +105,12 @@ class _Conv:
         self.act, self.slope = _ACT[act], float(slope)
 
     def problem(self, src, src_stride, dst, dst_stride, dst_off=0, shift=None, residual=None, residual_stride=0,
-                in_step=0, in_width=0):
+                in_step=0, in_width=0, out_step=0, out_width=0, tap_mask=0, dst_ptr_offset=0):
         wts = self.weights_tc if self.weights_tc is not None else self.weights
         return ConvProblem(src.data_ptr(), wts.data_ptr(), self.scale.data_ptr(),
-                           (self.shift if shift is None else shift).data_ptr(), dst.data_ptr(),
+                           (self.shift if shift is None else shift).data_ptr(), dst.data_ptr() + 4 * dst_ptr_offset,
                            None if residual is None else residual.data_ptr(), src_stride, dst_stride, dst_off, self.dil,
-                           residual_stride, in_step, in_width)
+                           residual_stride, in_step, in_width, out_step, out_width, tap_mask)
 
 
 class _Vortex:

@@ -65,7 +65,7 @@ def _run(case):
         t = [x.to(DEV), torch.from_numpy(packed).to(DEV), sc.to(DEV), sh.to(DEV), out, res.to(DEV) if use_res else None]
         keep.append(t)
         probs.append(ConvProblem(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), out.data_ptr(),
-                                 t[5].data_ptr() if use_res else None, istr, ostr, ocoff, d, cout if use_res else 0, 0, 0))
+                                 t[5].data_ptr() if use_res else None, istr, ostr, ocoff, d, cout if use_res else 0, 0, 0, 0, 0, 0))
         refs.append(y)
         outs.append(out)
     arr = (ConvProblem * nprob)(*probs)
@@ -96,7 +96,7 @@ def test_conv_tc_rejects_bad_arguments():
     L = _lib.lib()
     st = torch.cuda.current_stream().cuda_stream
     x = torch.zeros(128, 32, device=DEV)
-    p = ConvProblem(x.data_ptr() + 4, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), None, 32, 32, 0, 1, 0, 0, 0)
+    p = ConvProblem(x.data_ptr() + 4, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), None, 32, 32, 0, 1, 0, 0, 0, 0, 0, 0)
     arr = (ConvProblem * 1)(p)
     assert L.ojdf_conv_tc_batched(arr, 1, 32, 32, 8, 16, 1, 0, 0.0, 1.0, 0, 0, None, 0, st) == -1       # misaligned input
     assert L.ojdf_conv_tc_batched(arr, 1, 32, 32, 8, 16, 4, 0, 0.0, 1.0, 0, 0, None, 0, st) == -1       # taps not 1 or 9
@@ -120,11 +120,11 @@ def test_conv_tc_strided_input_matches_stride2_conv():
     _lib.check(L.ojdf_conv_tc_pack_weights(wc.ctypes.data, cin, cout, 1, 0, packed.ctypes.data))
     xd, pd, scd, shd = x.to(DEV), torch.from_numpy(packed).to(DEV), sc.to(DEV), sh.to(DEV)
     out = torch.full((Ho * Wo, cout), 7.0, device=DEV)
-    p = ConvProblem(xd.data_ptr(), pd.data_ptr(), scd.data_ptr(), shd.data_ptr(), out.data_ptr(), None, cin, cout, 0, 1, 0, 2, Win)
+    p = ConvProblem(xd.data_ptr(), pd.data_ptr(), scd.data_ptr(), shd.data_ptr(), out.data_ptr(), None, cin, cout, 0, 1, 0, 2, Win, 0, 0, 0)
     arr = (ConvProblem * 1)(p)
     _lib.check(L.ojdf_conv_tc_batched(arr, 1, cin, cout, Ho, Wo, 1, 1, 0.0, 1.0, 0, 0, None, 0, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert float((out.cpu().double() - ref).abs().max()) <= 5e-5 * float(ref.abs().max())
-    bad = ConvProblem(xd.data_ptr(), pd.data_ptr(), scd.data_ptr(), shd.data_ptr(), out.data_ptr(), None, cin, cout, 0, 1, 0, 2, Wo)
+    bad = ConvProblem(xd.data_ptr(), pd.data_ptr(), scd.data_ptr(), shd.data_ptr(), out.data_ptr(), None, cin, cout, 0, 1, 0, 2, Wo, 0, 0, 0)
     assert L.ojdf_conv_tc_batched((ConvProblem * 1)(bad), 1, cin, cout, Ho, Wo, 1, 1, 0.0, 1.0, 0, 0, None, 0,
                                   torch.cuda.current_stream().cuda_stream) == -1          # input row narrower than the reads

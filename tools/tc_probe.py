@@ -97,7 +97,7 @@ def run_case(idx, timing):
         t = [x.to(dev), torch.from_numpy(packed).to(dev), sc.to(dev), sh.to(dev), out, res.to(dev) if use_res else None]
         keep.append(t)
         probs.append(ConvProblem(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), out.data_ptr(),
-                                 t[5].data_ptr() if use_res else None, istr, ostr, ocoff, d, cout if use_res else 0, 0, 0))
+                                 t[5].data_ptr() if use_res else None, istr, ostr, ocoff, d, cout if use_res else 0, 0, 0, 0, 0, 0))
         refs.append(y)
         outs.append(out)
     arr = (ConvProblem * nprob)(*probs)
