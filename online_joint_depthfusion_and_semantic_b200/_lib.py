@@ -88,8 +88,18 @@ def require_cuda(*tensors):
                             'there is no CPU fallback' % t.device)
 
 
+_REPLAYED = 0
+
+
+def note_replayed(n):
+    """A CUDA-graph replay re-launched `n` libojdf kernels that the C-side counter only saw at capture time."""
+    global _REPLAYED
+    _REPLAYED += int(n)
+
+
 def launch_count():
-    return int(lib().ojdf_launch_count())
+    """libojdf kernels launched by this process: direct launches (C-side counter) + graph replays."""
+    return int(lib().ojdf_launch_count()) + _REPLAYED
 
 
 class KernelTimers:

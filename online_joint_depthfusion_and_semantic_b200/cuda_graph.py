@@ -8,6 +8,8 @@ Dropout inside the captured region keeps drawing fresh randoms on every replay (
 Philox offset of graph-registered generators)."""
 import torch
 
+from . import _lib
+
 
 class GraphedCall:
     """fn(*tensors) -> tensor or tuple of tensors, captured per (shapes, dtypes, device)."""
@@ -23,10 +25,11 @@ class GraphedCall:
         entry = self.cache.get(key)
         if entry is None:
             entry = self.cache[key] = self._capture(args)
-        graph, static_in, static_out = entry
+        graph, static_in, static_out, n_own = entry
         for s, a in zip(static_in, args):
             s.copy_(a, non_blocking=True)
         graph.replay()
+        _lib.note_replayed(n_own)
         return static_out
 
     def _capture(self, args):
@@ -39,6 +42,8 @@ class GraphedCall:
                 self.fn(*static_in)
         cur.wait_stream(side)
         graph = torch.cuda.CUDAGraph()
+        n0 = int(_lib.lib().ojdf_launch_count())
         with torch.cuda.graph(graph):
             static_out = self.fn(*static_in)
-        return graph, static_in, static_out
+        n_own = int(_lib.lib().ojdf_launch_count()) - n0          # libojdf kernels inside the captured graph
+        return graph, static_in, static_out, n_own
