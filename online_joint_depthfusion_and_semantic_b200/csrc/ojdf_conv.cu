@@ -315,7 +315,7 @@ channel_sum_kernel(const float *__restrict__ in, int in_stride, int npix, int C,
 // shift_out[co] = f_shift[co] + f_scale[co] * sum_c wf1[co,c] * v[c].   C <= 2048, Cg, Cout <= 256.
 // One block: the partial sums are folded with 4 independent accumulators per channel, the two small
 // matrix-vector products run one output per warp with lanes across the (contiguous) input index.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 gap_bias_kernel(const float *__restrict__ partial, int nblocks, int npix, int C,
                 const float *__restrict__ wg /* [Cg][C] */, const float *__restrict__ g_scale, const float *__restrict__ g_shift, int Cg,
                 int v_relu, const float *__restrict__ wf1 /* [Cout][Cg] */, const float *__restrict__ f_scale,
@@ -323,7 +323,7 @@ gap_bias_kernel(const float *__restrict__ partial, int nblocks, int npix, int C,
 {
     __shared__ float s_mean[2048];
     __shared__ float s_v[256];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
     for (int c = t; c < C; c += blockDim.x) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         int b = 0;
@@ -337,9 +337,18 @@ gap_bias_kernel(const float *__restrict__ partial, int nblocks, int npix, int C,
         s_mean[c] = ((s0 + s1) + (s2 + s3)) / (float)npix;
     }
     __syncthreads();
-    for (int o = warp; o < Cg; o += 8) {
-        float a = 0.0f;
-        for (int c = lane; c < C; c += 32) a = fmaf(__ldg(wg + (size_t)o * C + c), s_mean[c], a);
+    for (int o = warp; o < Cg; o += nwarps) {                  // one output per warp, four loads in flight per lane
+        const float *w = wg + (size_t)o * C;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int c = lane;
+        for (; c + 96 < C; c += 128) {
+            a0 = fmaf(__ldg(w + c), s_mean[c], a0);
+            a1 = fmaf(__ldg(w + c + 32), s_mean[c + 32], a1);
+            a2 = fmaf(__ldg(w + c + 64), s_mean[c + 64], a2);
+            a3 = fmaf(__ldg(w + c + 96), s_mean[c + 96], a3);
+        }
+        for (; c < C; c += 32) a0 = fmaf(__ldg(w + c), s_mean[c], a0);
+        float a = (a0 + a1) + (a2 + a3);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
         if (lane == 0) {
@@ -348,7 +357,7 @@ gap_bias_kernel(const float *__restrict__ partial, int nblocks, int npix, int C,
         }
     }
     __syncthreads();
-    for (int o = warp; o < Cout; o += 8) {
+    for (int o = warp; o < Cout; o += nwarps) {
         float a = 0.0f;
         for (int c = lane; c < Cg; c += 32) a = fmaf(__ldg(wf1 + (size_t)o * Cg + c), s_v[c], a);
 #pragma unroll
@@ -555,7 +564,7 @@ extern "C" int ojdf_gap_bias(const float *in_dev, int in_stride, int npix, int C
         channel_sum4_kernel<<<pb, 256, 0, s>>>(in_dev, in_stride, npix, C, partial_dev);
     else
         channel_sum_kernel<<<dim3(pb, (C + 255) / 256), 256, 0, s>>>(in_dev, in_stride, npix, C, partial_dev);
-    gap_bias_kernel<<<1, 256, 0, s>>>(partial_dev, pb, npix, C, wg_dev, g_scale_dev, g_shift_dev, Cg, v_relu, wf1_dev,
+    gap_bias_kernel<<<1, 1024, 0, s>>>(partial_dev, pb, npix, C, wg_dev, g_scale_dev, g_shift_dev, Cg, v_relu, wf1_dev,
                                      f_scale_dev, f_shift_dev, Cout, shift_out_dev);
     return launched(2);
 }
