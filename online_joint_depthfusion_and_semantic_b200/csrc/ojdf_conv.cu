@@ -324,17 +324,39 @@ gap_bias_kernel(const float *__restrict__ partial, int nblocks, int npix, int C,
     __shared__ float s_mean[2048];
     __shared__ float s_v[256];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
-    for (int c = t; c < C; c += blockDim.x) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int b = 0;
-        for (; b + 3 < nblocks; b += 4) {
-            s0 += partial[(size_t)b * C + c];
-            s1 += partial[(size_t)(b + 1) * C + c];
-            s2 += partial[(size_t)(b + 2) * C + c];
-            s3 += partial[(size_t)(b + 3) * C + c];
+    __shared__ float s_red[1024];
+    const int parts = C <= (int)blockDim.x ? (int)blockDim.x / C : 1;     // thread groups that share the partial blocks
+    if (parts > 1) {
+        const int c = t % C, part = t / C;
+        if (part < parts) {
+            float s0 = 0.f, s1 = 0.f;
+            int b = part;
+            for (; b + parts < nblocks; b += 2 * parts) {
+                s0 += partial[(size_t)b * C + c];
+                s1 += partial[(size_t)(b + parts) * C + c];
+            }
+            if (b < nblocks) s0 += partial[(size_t)b * C + c];
+            s_red[part * C + c] = s0 + s1;
         }
-        for (; b < nblocks; ++b) s0 += partial[(size_t)b * C + c];
-        s_mean[c] = ((s0 + s1) + (s2 + s3)) / (float)npix;
+        __syncthreads();
+        if (t < C) {
+            float a = 0.f;
+            for (int q = 0; q < parts; ++q) a += s_red[q * C + t];     // fixed order: deterministic
+            s_mean[t] = a / (float)npix;
+        }
+    } else {
+        for (int c = t; c < C; c += blockDim.x) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int b = 0;
+            for (; b + 3 < nblocks; b += 4) {
+                s0 += partial[(size_t)b * C + c];
+                s1 += partial[(size_t)(b + 1) * C + c];
+                s2 += partial[(size_t)(b + 2) * C + c];
+                s3 += partial[(size_t)(b + 3) * C + c];
+            }
+            for (; b < nblocks; ++b) s0 += partial[(size_t)b * C + c];
+            s_mean[c] = ((s0 + s1) + (s2 + s3)) / (float)npix;
+        }
     }
     __syncthreads();
     for (int o = warp; o < Cg; o += nwarps) {                  // one output per warp, four loads in flight per lane
@@ -557,7 +579,7 @@ extern "C" int ojdf_gap_bias(const float *in_dev, int in_stride, int npix, int C
     // few, fat partial blocks: the second stage (one block) walks them serially per channel
     int pb = npix / 128;
     if (pb < 8) pb = 8;
-    if (pb > 64) pb = 64;
+    if (pb > 148) pb = 148;
     if (pb > partial_blocks) pb = partial_blocks;
     if (pb > npix) pb = npix;
     if (!(C & 3) && C <= 1024 && !(in_stride & 3) && !((uintptr_t)in_dev & 15))
