@@ -108,3 +108,21 @@ def test_conv_tc_weight_packing_layout(L):
             assert img[g, t, kc, 1, r, chunk, k & 3] == lo[co, ci, t]
         assert np.count_nonzero(packed) <= 2 * w.size and not np.isnan(packed).any()
     assert L.ojdf_conv_tc_batched(None, 1, 32, 32, 8, 16, 1, 0, 0.0, 1.0, 0, 0, None, 0, None) == -1
+
+
+def test_conv_problem_struct_matches_header(tmp_path):
+    """The ctypes mirror of ojdf_conv_problem (modules/fusion_engine.py) has the size and field offsets the C
+    compiler gives include/ojdf.h."""
+    import subprocess
+    from online_joint_depthfusion_and_semantic_b200.modules.fusion_engine import ConvProblem
+    fields = [f[0] for f in ConvProblem._fields_]
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ojdf.h"\nint main(void) {\n'
+                   '  printf("%zu", sizeof(ojdf_conv_problem));\n' +
+                   ''.join('  printf(" %%zu", offsetof(ojdf_conv_problem, %s));\n' % f for f in fields) +
+                   '  return 0;\n}\n')
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    out = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == C.sizeof(ConvProblem)
+    assert out[1:] == [getattr(ConvProblem, f).offset for f in fields]

@@ -1,6 +1,8 @@
-"""Bring-up / regression probe for the tcgen05 tap-GEMM (csrc/ojdf_conv_tc.cu): each case runs in its own
-process (a trapped kernel must not take the others down), compares with an fp64 torch convolution and
-prints one line.  Usage on the GPU box:  python tools/tc_probe.py [--time]"""
+"""Bring-up / timing probe for the tcgen05 tap GEMM (csrc/ojdf_conv_tc.cu): each case runs in its own process
+(a trapped kernel must not take the others down), compares with an fp64 torch convolution and prints one line.
+Usage on the GPU box:  python tools/tc_probe.py [--time] [--only PREFIX]
+Case tuple: (name, H, W, cin, cout, taps, dil, in_stride, out_stride, out_coff, act, residual, n_problems, flags);
+bits 16-23 of flags = npad_req."""
 import ctypes as C
 import os
 import subprocess
@@ -9,58 +11,42 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-# (name, H, W, cin, cout, taps, dil, in_stride, out_stride, out_coff, act, residual, n_problems, flags)
 CASES = [
+    # correctness (also in tests/test_gpu_conv_tc.py)
     ('1x1 one tile one chunk', 8, 16, 32, 32, 1, 1, 32, 32, 0, 0, False, 1, 0),
-    ('1x1 one tile, hw-truncation flag', 8, 16, 32, 32, 1, 1, 32, 32, 0, 0, False, 1, 1),
     ('1x1 cin 19 of stride 116', 8, 16, 19, 19, 1, 1, 116, 20, 0, 2, False, 1, 0),
-    ('1x1 4 chunks', 16, 32, 114, 114, 1, 1, 116, 116, 0, 1, False, 1, 0),
     ('3x3 one tile', 8, 16, 32, 32, 9, 1, 32, 32, 0, 0, False, 1, 0),
     ('3x3 dense block', 48, 64, 95, 19, 9, 1, 116, 116, 95, 2, False, 2, 0),
     ('3x3 dil 3 ragged image', 37, 53, 19, 19, 9, 3, 20, 20, 0, 1, False, 4, 0),
     ('3x3 dil 27', 48, 64, 19, 19, 9, 27, 20, 20, 0, 1, False, 8, 0),
-    ('1x1 570 -> 114', 48, 64, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 0),
     ('1x1 -> 9 tanh', 48, 64, 19, 9, 1, 1, 116, 9, 0, 3, False, 1, 0),
     ('1x1 256 out (2 groups) residual sigmoid', 30, 40, 256, 256, 1, 1, 256, 256, 0, 4, True, 1, 0),
-    ('3x3 240x320 dense block', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 0),
-    ('3x3 240x320 19->19', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 0),
-    ('1x1 240x320 456->114', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 0),
-    ('1x1 240x320 114->95', 240, 320, 114, 95, 1, 1, 116, 116, 0, 2, False, 1, 0),
-    ('1x1 240x320 19->19 into 456', 240, 320, 19, 19, 1, 1, 20, 456, 57, 1, False, 8, 0),
-    ('3x3 60x80 64->64 dil 2 residual', 60, 80, 64, 64, 9, 2, 64, 64, 0, 1, True, 2, 0),
-    ('3x3 15x20 512->512 (4 groups)', 15, 20, 512, 512, 9, 1, 512, 512, 0, 1, False, 1, 0),
     ('3x3 30x40 64->64 dil 2 halo', 30, 40, 64, 64, 9, 2, 64, 64, 0, 1, False, 1, 0),
     ('3x3 dense block, per-tap boxes', 48, 64, 95, 19, 9, 1, 116, 116, 95, 2, False, 2, 4),
     ('3x3 dense block, MT=1', 48, 64, 95, 19, 9, 1, 116, 116, 95, 2, False, 2, 2),
-    ('3x3 dense block, plain stores', 48, 64, 95, 19, 9, 1, 116, 116, 95, 2, False, 2, 8),
-    ('1x1 aligned TMA store 20 of 24 at 4', 48, 64, 64, 20, 1, 1, 64, 28, 4, 1, False, 2, 0),
-    ('T: dense 240x320 no MMA', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 16),
-    ('T: dense 240x320 no split', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 32),
-    ('T: dense 240x320 no MMA no split', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 48),
-    ('T: dense 240x320 1xTF32', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 64),
-    ('T: dense 240x320 MT=1', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 2),
-    ('T: 456->114 no MMA', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 16),
-    ('T: 456->114 no split', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 32),
-    ('T: 456->114 no MMA no split', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 48),
-    ('T: 456->114 1xTF32', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 64),
-    ('P: dense', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 128),
-    ('P: dense no MMA no split', 240, 320, 114, 19, 9, 1, 116, 116, 0, 2, False, 2, 128 | 48),
-    ('P: 456->114', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128),
-    ('P: 456->114 no MMA no split', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 48),
-    ('P: 19->19 3x3', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 128),
-    ('P: 114->95', 240, 320, 114, 95, 1, 1, 116, 116, 0, 2, False, 1, 128),
-    ('K: 1x1 15x20 1024->256 x2', 15, 20, 1024, 256, 1, 1, 1024, 512, 0, 1, False, 2, 0),
-    ('K: 1x1 15x20 1024->256 x2 no split', 15, 20, 1024, 256, 1, 1, 1024, 512, 0, 1, False, 2, 4096),
-    ('K: 1x1 15x20 1024->256 x2 npad32 no split', 15, 20, 1024, 256, 1, 1, 1024, 512, 0, 1, False, 2, 4096 | (32 << 16)),
-    ('K: 3x3 15x20 512->256 x4 dil 2/4', 15, 20, 512, 256, 9, 4, 512, 512, 0, 1, False, 4, 0),
-    ('K: 3x3 15x20 512->256 x4 no split npad32', 15, 20, 512, 256, 9, 4, 512, 512, 0, 1, False, 4, 4096 | (32 << 16)),
-    ('K: 1x1 15x20 512->2048 x2 residual', 15, 20, 512, 2048, 1, 1, 512, 2048, 0, 1, True, 2, 0),
-    ('K: 1x1 15x20 512->2048 x2 residual npad64 no split', 15, 20, 512, 2048, 1, 1, 512, 2048, 0, 1, True, 2, 4096 | (64 << 16)),
-    ('K: 3x3 60x80 280->256', 60, 80, 280, 256, 9, 1, 280, 256, 0, 1, False, 1, 0),
-    ('K: 3x3 60x80 280->256 npad64', 60, 80, 280, 256, 9, 1, 280, 256, 0, 1, False, 1, 64 << 16),
-    ('K: 3x3 60x80 64->64 x2', 60, 80, 64, 64, 9, 1, 64, 64, 0, 1, False, 2, 0),
-    ('K: 1x1 60x80 256->64 x2', 60, 80, 256, 64, 1, 1, 256, 64, 0, 1, False, 2, 0),
-    ('K: 1x1 60x80 64->256 x2 residual', 60, 80, 64, 256, 1, 1, 64, 256, 0, 1, True, 2, 0),
+    ('3x3 dense block, per-thread stores', 48, 64, 95, 19, 9, 1, 116, 116, 95, 2, False, 2, 8),
+    # FusionNet layer shapes at 240x320 (flag 1: padded channel groups -> TMA-store epilogue)
+    ('F: 3x3 114->19 x2 (dense block)', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 1),
+    ('F: 3x3 19->19 x2', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 1),
+    ('F: 1x1 456->114 x2 (vortex final)', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 1),
+    ('F: 1x1 114->95 (pred)', 240, 320, 114, 95, 1, 1, 116, 116, 0, 2, False, 1, 1),
+    ('F: 1x1 19->114 into 464 x8 (vortex branch out)', 240, 320, 19, 114, 1, 1, 20, 464, 116, 1, False, 8, 1),
+    ('F: 3x3 19->19 x8 dilations 27/26', 240, 320, 19, 19, 9, 27, 20, 20, 0, 1, False, 8, 1),
+    # AdapNet++ layer shapes
+    ('A: 1x1 15x20 1024->256 x2 (split K)', 15, 20, 1024, 256, 1, 1, 1024, 512, 0, 1, False, 2, 0),
+    ('A: 1x1 15x20 1024->256 x2, no split', 15, 20, 1024, 256, 1, 1, 1024, 512, 0, 1, False, 2, 4096),
+    ('A: 3x3 15x20 512->256 x4 dil 4/3 (split K)', 15, 20, 512, 256, 9, 4, 512, 512, 0, 1, False, 4, 0),
+    ('A: 1x1 15x20 512->2048 x2 residual', 15, 20, 512, 2048, 1, 1, 512, 2048, 0, 1, True, 2, 0),
+    ('A: 3x3 60x80 280->256 (decoder stage 3)', 60, 80, 280, 256, 9, 1, 280, 256, 0, 1, False, 1, 0),
+    ('A: 3x3 60x80 64->64 x2 (layer1)', 60, 80, 64, 64, 9, 1, 64, 64, 0, 1, False, 2, 0),
+    ('A: 1x1 60x80 64->256 x2 residual', 60, 80, 64, 256, 1, 1, 64, 256, 0, 1, True, 2, 0),
+    ('A: 3x3 30x40 48->4 relu (SSMA)', 30, 40, 48, 4, 9, 1, 48, 4, 0, 1, False, 1, 1),
+    # role profile / timing experiments (flag 128 = per-role wait cycles of block 0; 16 = no MMAs, 32 = no split
+    # work, 64 = 1xTF32, 1024 = busy-poll the A ring, 2048 = single accumulator set)
+    ('P: dense', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 128 | 1),
+    ('P: dense no MMA no split', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 128 | 48 | 1),
+    ('P: 456->114', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 1),
+    ('P: 456->114 no MMA no split', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 48 | 1),
 ]
 FN = 'ojdf_conv_tc_batched'
 
