@@ -187,6 +187,18 @@ int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int n_problems,
 /* nn.AvgPool2d(3, stride 1, padding 1) of VortexPooling (modules/model.py:114-116), C % 4 == 0. */
 int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int W, int C, float *out_dev, int out_stride,
                        void *stream);
+/* Up to 8 equally shaped 3x3 average pools (stride 1, zero padding counted in the divisor) in one launch; a problem
+ * with scale_dev != NULL also applies out = [relu](scale[c] * pool + shift[c]) (scale/shift: C floats, 16-byte
+ * aligned).  Used for VortexPooling's cascaded pools, which commute with the branch's first 1x1 convolution
+ * (modules/model.py:114-135): the engine pools W.x (19 channels) instead of x (114 channels). */
+typedef struct ojdf_pool_problem {
+    const float *in_dev;
+    float *out_dev;
+    const float *scale_dev;
+    const float *shift_dev;
+    int in_stride, out_stride;
+} ojdf_pool_problem;
+int ojdf_avgpool3_batched(const ojdf_pool_problem *problems_host, int n_problems, int H, int W, int C, int relu, void *stream);
 /* VortexPooling global branch (modules/model.py:107-112) folded into the bias of the `final` 1x1 conv:
  * shift_out[co] = f_shift[co] + f_scale[co] * sum_c wf1[co,c] * (g_scale[c]*(wg[c,:].mean_pixels(in)) + g_shift[c]).
  * partial_dev: scratch of partial_blocks*C floats. */

@@ -35,6 +35,7 @@ _SIGNATURES = {
     'ojdf_conv_tc_pack_weights': (_i, [_vp, _i, _i, _i, _i, _vp]),
     'ojdf_conv_tc_batched': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _i, _vp, _sz, _vp]),
     'ojdf_avgpool3_nhwc': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    'ojdf_avgpool3_batched': (_i, [_vp, _i, _i, _i, _i, _i, _vp]),
     'ojdf_vortex_bias': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp]),
     'ojdf_gap_bias': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp]),
     'ojdf_nchw_to_nhwc': (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),

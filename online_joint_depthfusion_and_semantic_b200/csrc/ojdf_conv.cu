@@ -254,6 +254,45 @@ avgpool3_kernel(const float *__restrict__ in, int in_stride, int H, int W, int C
     reinterpret_cast<float4 *>(out + (size_t)p * out_stride)[c4] = make_float4(s.x / 9.0f, s.y / 9.0f, s.z / 9.0f, s.w / 9.0f);
 }
 
+// Up to 8 independent 3x3 average pools of equal shape in one launch, with an optional per-channel
+// scale/shift (+ ReLU) on the way out.  VortexPooling feeds branch b with pool^b(x) followed by a 1x1
+// convolution + BatchNorm + ReLU (modules/model.py:114-135); pooling and the 1x1 convolution are both linear and
+// the zero padding maps to zero, so W.pool^b(x) = pool^b(W.x): the engine pools the 19-channel product instead
+// of the 114-channel input and applies bias / BatchNorm / ReLU here, after the last pool of the cascade.
+struct PoolProblem {
+    const float *in; float *out; const float *scale; const float *shift;      // scale == nullptr: plain pool
+    int in_stride, out_stride;
+};
+struct PoolBatch { PoolProblem p[kMaxBatch]; };
+
+__global__ void __launch_bounds__(256)
+avgpool3_batched_kernel(PoolBatch batch, int H, int W, int C, int relu)
+{
+    const PoolProblem pr = batch.p[blockIdx.y];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c4n = C >> 2;
+    if (i >= (long long)H * W * c4n) return;
+    const int c4 = (int)(i % c4n);
+    const int p = (int)(i / c4n), y = p / W, x = p - y * W;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int yy = y + dy, xx = x + dx;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(pr.in + (size_t)(yy * W + xx) * pr.in_stride) + c4);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    float4 o = make_float4(s.x / 9.0f, s.y / 9.0f, s.z / 9.0f, s.w / 9.0f);
+    if (pr.scale) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(pr.scale) + c4), b = __ldg(reinterpret_cast<const float4 *>(pr.shift) + c4);
+        o.x = fmaf(o.x, a.x, b.x); o.y = fmaf(o.y, a.y, b.y); o.z = fmaf(o.z, a.z, b.z); o.w = fmaf(o.w, a.w, b.w);
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    }
+    reinterpret_cast<float4 *>(pr.out + (size_t)p * pr.out_stride)[c4] = o;
+}
+
 // Per-channel sums over all pixels (global average pool numerator): block b sums its contiguous slice of
 // pixels with float4 loads (thread = one float4 column of one of `lanes` interleaved pixels), folds the
 // pixel lanes through shared memory in a fixed order and writes partial[b][C]; the tiny second stage runs
@@ -563,6 +602,24 @@ extern "C" int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int
         return OJDF_ERR_BADARG;
     const long long n = (long long)H * W * (C >> 2);
     avgpool3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in_dev, in_stride, H, W, C, out_dev, out_stride);
+    return launched(1);
+}
+
+extern "C" int ojdf_avgpool3_batched(const ojdf_pool_problem *problems_host, int n_problems, int H, int W, int C, int relu,
+                                     void *stream)
+{
+    if (!problems_host || n_problems < 1 || n_problems > kMaxBatch || H < 1 || W < 1 || C < 4 || (C & 3)) return OJDF_ERR_BADARG;
+    PoolBatch b;
+    for (int i = 0; i < kMaxBatch; ++i) {
+        const ojdf_pool_problem &q = problems_host[i < n_problems ? i : 0];
+        if (i < n_problems && (!q.in_dev || !q.out_dev || (q.in_stride & 3) || (q.out_stride & 3) || q.in_stride < C ||
+                               q.out_stride < C || (q.scale_dev && !q.shift_dev) || ((uintptr_t)q.in_dev & 15) ||
+                               ((uintptr_t)q.out_dev & 15) || ((uintptr_t)q.scale_dev & 15) || ((uintptr_t)q.shift_dev & 15)))
+            return OJDF_ERR_BADARG;
+        b.p[i] = PoolProblem{q.in_dev, q.out_dev, q.scale_dev, q.shift_dev, q.in_stride, q.out_stride};
+    }
+    const long long n = (long long)H * W * (C >> 2);
+    avgpool3_batched_kernel<<<dim3((unsigned)((n + 255) / 256), n_problems), 256, 0, (cudaStream_t)stream>>>(b, H, W, C, relu);
     return launched(1);
 }
 

@@ -6,8 +6,10 @@ test_fusion.py:63-65); this class turns them into a launch plan over pixel-major
   * per conv: weights re-laid out as [out-group of 20][tap][cin padded to 4][20], conv bias +
     inference BatchNorm folded into a per-channel (scale, shift) epilogue, activation fused;
   * dense-block concatenation (modules/model.py:258-263) = channel offsets into one buffer;
-  * VortexPooling (modules/model.py:100-161): 3 cascaded 3x3 average pools, 4 dilated branches writing
-    into one 4*C buffer, the global-pool branch folded into the bias of the `final` 1x1 conv;
+  * VortexPooling (modules/model.py:100-161): the 3 cascaded 3x3 average pools commute with the first 1x1 conv
+    of their branch, so the 19-channel product W.x is pooled (3 batched launches, BN + ReLU after the last pool)
+    instead of the 114-channel input; 4 dilated branches writing into one 4*C buffer; the global-pool branch
+    folded into the bias of the `final` 1x1 conv;
   * Pred chain (modules/model.py:24-52) ends in tanh * output_scale and writes (N, n_points) f32 --
     exactly the layout the integrator consumes, so no NCHW<->NHWC permutes exist anywhere.
 
@@ -67,10 +69,16 @@ class ConvProblem(C.Structure):
                 ('in_width', C.c_int), ('out_step', C.c_int), ('out_width', C.c_int), ('tap_mask', C.c_int)]
 
 
+class PoolProblem(C.Structure):
+    """include/ojdf.h: ojdf_pool_problem."""
+    _fields_ = [('in_dev', C.c_void_p), ('out_dev', C.c_void_p), ('scale_dev', C.c_void_p), ('shift_dev', C.c_void_p),
+                ('in_stride', C.c_int), ('out_stride', C.c_int)]
+
+
 class _Conv:
     """One fused conv (+BN) (+activation): weights re-laid out for conv_tile_kernel."""
 
-    def __init__(self, conv, bn, act, device, cin_slice=None, slope=0.01, tc=None, cin_map=None, npad_req=0):
+    def __init__(self, conv, bn, act, device, cin_slice=None, slope=0.01, tc=None, cin_map=None, npad_req=0, raw=False):
         w = conv.weight.detach().double().cpu()                 # (cout, cin, kh, kw); all folding on the host in f64
         if cin_slice is not None:
             w = w[:, cin_slice[0]:cin_slice[1]]
@@ -97,6 +105,8 @@ class _Conv:
             t = (bias - bn.running_mean.detach().double().cpu()) * s + bn.bias.detach().double().cpu()
         else:
             s, t = torch.ones(cout, dtype=torch.float64), bias
+        if raw:                                                # the bare product W.x: bias / BatchNorm / activation applied later
+            s, t, act = torch.ones(cout, dtype=torch.float64), torch.zeros(cout, dtype=torch.float64), 'none'
         self.weights = prep.float().contiguous().to(device)
         self.npad_req = int(npad_req)
         self.weights_tc = pack_tc_weights(w, self.npad_req).to(device) if (conv_mode() == 'tc' if tc is None else tc) else None
@@ -121,6 +131,15 @@ class _Vortex:
         self.cin = in_map[1]                                    # padded input width
         self.branches = [[_Conv(br[0], br[1], 'relu', device, cin_map=in_map), _Conv(br[3], br[4], 'relu', device),
                           _Conv(br[6], br[7], 'relu', device), _Conv(br[9], br[10], 'relu', device)] for br in m.branches]
+        # branches 1..3 see pool^b(x); their first 1x1 conv commutes with the pools, so it runs on x itself without
+        # bias / BatchNorm / ReLU (`raw`), and those are applied after the last pool (scale / shift below, padded to 4)
+        self.raw = [None] + [_Conv(br[0], None, 'none', device, cin_map=in_map, raw=True) for br in list(m.branches)[1:]]
+        self.post = [None]
+        for b in range(1, 4):
+            f = self.branches[b][0]
+            sc, sh = torch.zeros(_pad4(f.cout), device=device), torch.zeros(_pad4(f.cout), device=device)
+            sc[:f.cout], sh[:f.cout] = f.scale, f.shift
+            self.post.append((sc, sh))
         fin_conv, fin_bn = m.final[0], m.final[1]
         C_ = self.cout
         # the 4 branch outputs, each in its own 4-aligned group of the branch buffer
@@ -202,19 +221,29 @@ class FusionNetEngine:
             n = len(vs)
             cin, Cv = vs[0].cin, vs[0].cout
             ps, Cvp = _pad4(cin), _pad4(Cv)
-            pools = [[z(ps) for _ in range(3)] for _ in range(n)]
             tb = [[[z(mid_s) for _ in range(2)] for _ in range(4)] for _ in range(n)]
+            Y = [[None] + [z(mid_s) for _ in range(3)] for _ in range(n)]          # W_b . x, b = 1..3
+            P1 = [[None, None] + [z(mid_s) for _ in range(2)] for _ in range(n)]   # pool(Y_b), b = 2, 3
+            P2 = [z(mid_s) for _ in range(n)]                                       # pool(pool(Y_3))
             br_out = [z(4 * Cvp) for _ in range(n)]
-            self._keep += [pools, tb, br_out]
+            self._keep += [tb, Y, P1, P2, br_out]
             for i, v in enumerate(vs):
                 self.plan.append(('bias', v, srcs[i], src_stride))
-                cur, cs = srcs[i], src_stride
-                for k in range(3):                              # cascaded 3x3 average pools
-                    self.plan.append(('pool', cur, cs, ps, pools[i][k], ps))
-                    cur, cs = pools[i][k], ps
-            ins = [[(srcs[i], src_stride)] + [(pools[i][k], ps) for k in range(3)] for i in range(n)]
-            conv_step([(vs[i].branches[b][0], vs[i].branches[b][0].problem(ins[i][b][0], ins[i][b][1], tb[i][b][0], mid_s))
-                       for i in range(n) for b in range(4)])
+            # branch 0: 1x1 + BN + ReLU on x; branches 1..3: the bare 1x1 product on x, then the cascaded pools
+            conv_step([(vs[i].branches[0][0], vs[i].branches[0][0].problem(srcs[i], src_stride, tb[i][0][0], mid_s)) for i in range(n)])
+            conv_step([(vs[i].raw[b], vs[i].raw[b].problem(srcs[i], src_stride, Y[i][b], mid_s)) for i in range(n) for b in (1, 2, 3)])
+
+            def pool_step(items):
+                """items: (src, dst, (scale, shift) or None); one launch, ReLU where an epilogue is given."""
+                arr = (PoolProblem * len(items))(*[PoolProblem(a.data_ptr(), d.data_ptr(), e[0].data_ptr() if e else None,
+                                                               e[1].data_ptr() if e else None, mid_s, mid_s) for a, d, e in items])
+                self._keep.append([e for _, _, e in items])
+                self.plan.append(('pools', arr, len(items), mid_s))
+
+            pool_step([(Y[i][1], tb[i][1][0], vs[i].post[1]) for i in range(n)] +
+                      [(Y[i][b], P1[i][b], None) for i in range(n) for b in (2, 3)])
+            pool_step([(P1[i][2], tb[i][2][0], vs[i].post[2]) for i in range(n)] + [(P1[i][3], P2[i], None) for i in range(n)])
+            pool_step([(P2[i], tb[i][3][0], vs[i].post[3]) for i in range(n)])
             conv_step([(vs[i].branches[b][1], vs[i].branches[b][1].problem(tb[i][b][0], mid_s, tb[i][b][1], mid_s))
                        for i in range(n) for b in range(4)])
             conv_step([(vs[i].branches[b][2], vs[i].branches[b][2].problem(tb[i][b][1], mid_s, tb[i][b][0], mid_s))
@@ -273,6 +302,9 @@ class FusionNetEngine:
                         _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, 0, 1, None, 0, st))   # 1: pads are ours
                     else:
                         _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, None, 0, st))
+                elif kind == 'pools':
+                    _, arr, n, ch = step
+                    _lib.check(L.ojdf_avgpool3_batched(arr, n, H, W, ch, 1, st))
                 elif kind == 'pool':
                     _, src, ss, ch, dst, ds = step
                     _lib.check(L.ojdf_avgpool3_nhwc(src.data_ptr(), ss, H, W, ch, dst.data_ptr(), ds, st))
