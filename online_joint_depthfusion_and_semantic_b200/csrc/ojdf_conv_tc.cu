@@ -14,16 +14,23 @@
 //     serves all 9 taps; huge dilations (halo would not fit) fall back to one box per tap;
 //   * the A operand lives in TENSOR MEMORY: eight "splitter" warps read the tap-shifted pixel rows out
 //     of the swizzled halo tile (conflict-free LDS.128), split them into hi/lo in registers and
-//     tcgen05.st both halves into a 4-deep TMEM ring; tcgen05.mma reads A from TMEM and only the small
+//     tcgen05.st both halves into a ring of TMEM stages (2-3 per issuer); tcgen05.mma reads A from TMEM and only the small
 //     weight tiles (B, K-major SWIZZLE_128B images packed by the host) from shared memory -- shared
 //     memory carries each activation byte once per tap instead of five times;
 //   * one weight stage (tap, K chunk) is reused by all MT M-tiles of the group;
 //   * accumulators are double buffered in TMEM (when 2*MT*NPAD <= 256 columns) so the epilogue of one
 //     group (tcgen05.ld -> scale/shift/residual/activation -> swizzled staging tile -> TMA store, clipped
-//     by the tensor map to the image and to channels < coff+cout) overlaps the main loop of the next.
+//     by the tensor map to the image and to channels < coff+cout) overlaps the main loop of the next;
+//   * stride-2 layers read every other pixel through the input tensor map (in_step), the phases of a transposed
+//     convolution write every s-th pixel through the output tensor map (out_step) with their dead taps masked;
+//   * feature maps too small to give every SM an M-tile (AdapNet++ at 15x20) split the K loop over CTAs, raw
+//     partial sums go to a scratch buffer and conv_reduce_kernel (ojdf_conv.cu) finishes the layer in a fixed order;
+//   * programmatic dependent launch: barrier set-up and the TMEM allocation overlap the previous layer's tail.
 // Warp roles (608 threads): 0 = TMA producer, 1 and 18 = MMA issuers (even / odd M-tiles of a group; warp 1
-// also owns the TMEM allocation), 2..9 = splitters (two sets of four, alternating A stages), 10..17 =
-// epilogue (two warps per TMEM lane quarter, alternating 16-column chunks).
+// also owns the TMEM allocation), 2..9 = splitters (two sets of four; set p feeds issuer p through its own
+// in-order ring of A stages -- two consumers alternating on one mbarrier would alias its parity), 10..17 =
+// epilogue (two warps per TMEM lane quarter, alternating 16-column chunks).  Every role walks the same
+// deterministic sequence of work groups (decode()), so no tile scheduler state is shared.
 #include <cuda.h>
 
 #include <cstdio>
