@@ -14,6 +14,8 @@ with `.volume`, `.origin`, `.resolution`, `.bbox` -- what modules/database.py:48
 import numpy as np
 import torch
 
+from . import metrics
+
 
 class Voxelgrid:
     """The four attributes of deps/graphics Voxelgrid the hot path touches (voxelgrid.py:54-70,157-161)."""
@@ -42,6 +44,8 @@ class Database:
         self.initial_value = config.init_value
         self.semantics = config.semantics
         self.semantic_grid = getattr(config, 'semantic_grid', False)
+        if self.semantics:
+            self.n_classes = getattr(config, 'n_classes', None)
         self.scenes, self.state, self.origin, self.resolution = [], {}, {}, {}
         self.scenes_gt, self.scenes_est, self.fusion_weights = {}, {}, {}
         self.ids_gt, self.ids_est, self.scores = {}, {}, {}
@@ -98,3 +102,42 @@ class Database:
             low = self.fusion_weights[s] < value
             self.scenes_est[s].volume[low] = self.initial_value
             self.fusion_weights[s][low] = 0
+
+    def filter_semantics(self, value=5):
+        """modules/database.py:114-116 (scipy median filter of the label volume), on the device."""
+        for s in self.scenes:
+            self.ids_est[s].volume = metrics.median_filter_labels(self.ids_est[s].volume, size=value)
+
+    def evaluate(self, mode='train', workspace=None):
+        """modules/database.py:265-310: mse / mad / iou / acc (+ 'f1') averaged over the scenes, without leaving
+        the device.  mode == 'test' also returns the per-scene results."""
+        total, per_scene = {}, {}
+        for s in self.scenes:
+            if not self.state[s]:
+                continue
+            r = metrics.evaluation(self.scenes_est[s].volume, self.scenes_gt[s].volume, self.fusion_weights[s] > 0)
+            per_scene[s] = r
+            for k, v in r.items():
+                if workspace is not None:
+                    workspace.log('{} {}'.format(k, v), mode)
+                total[k] = total.get(k, 0.0) + v
+        for k in total:
+            total[k] /= len(self.scenes_est)
+        return (total, per_scene) if mode == 'test' else total
+
+    def evaluate_semantics(self, mode='train', workspace=None):
+        """modules/database.py:312-349: mean class accuracy / mean IoU of the label volumes."""
+        total, per_scene = {}, {}
+        for s in self.scenes:
+            if not self.state[s]:
+                continue
+            r, cls_iou = metrics.semantic_evaluation(self.ids_est[s].volume, self.ids_gt[s].volume,
+                                                     self.fusion_weights[s] > 0, self.n_classes)
+            per_scene[s] = cls_iou
+            for k, v in r.items():
+                if workspace is not None:
+                    workspace.log('{} {}'.format(k, v), mode)
+                total[k] = total.get(k, 0.0) + v
+        for k in total:
+            total[k] /= len(self.scenes_est)
+        return total, per_scene
