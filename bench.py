@@ -140,7 +140,7 @@ def build_world(device, rank, h=H, w=W, grid=GRID, scenes_per_rank=SCENES_PER_RA
                              seed=rank * scenes_per_rank + i, intrinsics='pinhole')
               for i in range(scenes_per_rank)]
     db = Database(SceneSet(scenes, device), Config(device=device, implementation='efficient', init_value=0.1,
-                                                   semantics='class30', semantic_grid=True))
+                                                   semantics='class30', semantic_grid=True, n_classes=N_CLASSES))
     rd = render_device or device
     host_frames = []
     for f in range(frames):
