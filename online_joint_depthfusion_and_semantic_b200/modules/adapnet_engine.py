@@ -42,6 +42,31 @@ def _npad_for(cout, n_problems, n_tiles=4):
     return 0
 
 
+def deconv_phase_weights(weight, stride, padding):
+    """ConvTranspose2d(kernel 2s, stride s, padding s/2) as s*s phase convolutions (pure host logic).
+
+    weight: (cin, cout, k, k) of the transposed convolution.  Output pixel (s*y + a, s*x + b) is a 3x3 window of
+    the input around (y, x): in[y + dy, x + dx] meets kernel tap ky = a + p - s*dy, kx = b + p - s*dx when that tap
+    exists (2 per axis, 4 of the 9).  Returns [(a, b, w3x3 (cout, cin, 3, 3), tap_mask)] in phase order a*s + b;
+    bit t = (dy+1)*3 + (dx+1) of tap_mask is set for the live taps."""
+    cin, cout, k, _ = weight.shape
+    s, p = int(stride), int(padding)
+    assert k == 2 * s and 2 * p == s
+    phases = []
+    for a in range(s):
+        for b in range(s):
+            wp, mask = torch.zeros(cout, cin, 3, 3, dtype=weight.dtype), 0
+            for dy in (-1, 0, 1):
+                ky = a + p - s * dy
+                for dx in (-1, 0, 1):
+                    kx = b + p - s * dx
+                    if 0 <= ky < k and 0 <= kx < k:
+                        wp[:, :, dy + 1, dx + 1] = weight[:, :, ky, kx].t()
+                        mask |= 1 << ((dy + 1) * 3 + dx + 1)
+            phases.append((a, b, wp, mask))
+    return phases
+
+
 def _Conv(conv, bn, act, device, n_problems=2, n_tiles=4, **kw):
     tc = conv_mode() == 'tc'
     return _ConvBase(conv, bn, act, device, tc=tc,
@@ -332,28 +357,19 @@ class AdapNetEngine:
             output pixel (s*y + a, s*x + b) = 3x3 window of the input around (y, x) with the kernel taps
             ky = a + p - s*dy, kx = b + p - s*dx that exist (4 of the 9); each phase is one problem of the
             tensor-core kernel writing every s-th pixel of the output (out_step), dead taps masked."""
-            sdc, k, pad = int(m.stride[0]), int(m.kernel_size[0]), int(m.padding[0])
-            assert k == 2 * sdc and 2 * pad == sdc and int(m.output_padding[0]) == 0
+            sdc, pad = int(m.stride[0]), int(m.padding[0])
+            assert int(m.output_padding[0]) == 0
             Wt = m.weight.detach().cpu()                                  # (cin, cout, k, k)
             cin, cout = Wt.shape[:2]
             Wout = Win * sdc
             pairs = []
-            for a in range(sdc):
-                for b in range(sdc):
-                    fake = torch.nn.Conv2d(cin, cout, 3, padding=1, bias=True)
-                    wp, mask = torch.zeros(cout, cin, 3, 3), 0
-                    for dy in (-1, 0, 1):
-                        ky = a + pad - sdc * dy
-                        for dx in (-1, 0, 1):
-                            kx = b + pad - sdc * dx
-                            if 0 <= ky < k and 0 <= kx < k:
-                                wp[:, :, dy + 1, dx + 1] = Wt[:, :, ky, kx].t()
-                                mask |= 1 << ((dy + 1) * 3 + dx + 1)
-                    fake.weight.data.copy_(wp)
-                    fake.bias.data.copy_(m.bias.detach().cpu() if m.bias is not None else torch.zeros(cout))
-                    c = mk(fake, bn, act, Hin, Win, sdc * sdc)
-                    pairs.append((c, c.problem(src, src_stride, dst, dst_stride, 0, out_step=sdc, out_width=Wout,
-                                               tap_mask=mask, dst_ptr_offset=(a * Wout + b) * dst_stride)))
+            for a, b, wp, mask in deconv_phase_weights(Wt, sdc, pad):
+                fake = torch.nn.Conv2d(cin, cout, 3, padding=1, bias=True)
+                fake.weight.data.copy_(wp)
+                fake.bias.data.copy_(m.bias.detach().cpu() if m.bias is not None else torch.zeros(cout))
+                c = mk(fake, bn, act, Hin, Win, sdc * sdc)
+                pairs.append((c, c.problem(src, src_stride, dst, dst_stride, 0, out_step=sdc, out_width=Wout,
+                                           tap_mask=mask, dst_ptr_offset=(a * Wout + b) * dst_stride)))
             for i in range(0, len(pairs), 8):
                 conv_step(pairs[i:i + 8], Hin, Win)
 

@@ -1,0 +1,63 @@
+"""Host-side logic of the network engines that needs no GPU: the phase decomposition of the decoder's transposed
+convolutions, the padded channel-group maps with their zero weight rows, and the pool / 1x1-conv commutation the
+FusionNet engine relies on (modules/adapnet_engine.py, modules/fusion_engine.py)."""
+import numpy as np
+import pytest
+import torch
+from torch.nn import functional as F
+
+from online_joint_depthfusion_and_semantic_b200.modules.adapnet_engine import deconv_phase_weights
+from online_joint_depthfusion_and_semantic_b200.modules.fusion_engine import _Conv, group_map
+
+
+@pytest.mark.parametrize('k,s,p,cin,cout', [(4, 2, 1, 5, 7), (8, 4, 2, 6, 3)])
+def test_transposed_conv_equals_its_phase_convolutions(k, s, p, cin, cout):
+    """Decoder.deconv1 / stage2[6] (k=4, s=2, p=1) and stage3[8] (k=8, s=4, p=2), modules/adapnet.py:138-148."""
+    g = torch.Generator().manual_seed(k)
+    x = torch.randn(1, cin, 9, 11, generator=g, dtype=torch.float64)
+    w = torch.randn(cin, cout, k, k, generator=g, dtype=torch.float64)
+    ref = F.conv_transpose2d(x, w, stride=s, padding=p)
+    out = torch.zeros_like(ref)
+    phases = deconv_phase_weights(w, s, p)
+    assert len(phases) == s * s
+    for a, b, wp, mask in phases:
+        assert bin(mask).count('1') == 4                       # two live taps per axis
+        for t in range(9):
+            if not (mask >> t) & 1:
+                assert float(wp[:, :, t // 3, t % 3].abs().max()) == 0.0
+        out[:, :, a::s, b::s] = F.conv2d(x, wp, padding=1)
+    assert float((out - ref).abs().max()) < 1e-12
+
+
+def test_group_map_and_zero_weight_rows():
+    """Dense-block buffer of FusionNet: 19-channel groups at pitch 20 (fusion_engine.py); the consumer's expanded
+    weights must reproduce conv + BatchNorm of the unpadded tensor whatever the pad channels hold."""
+    pos, width = group_map(3, 19)
+    assert width == 60 and pos[:3] == [0, 1, 2] and pos[19] == 20 and pos[38] == 40 and len(pos) == 57
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(57, 19, 1)
+    bn = torch.nn.BatchNorm2d(19).eval()
+    bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 1.5); bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_()
+    c = _Conv(conv, bn, 'none', 'cpu', tc=False, cin_map=(pos, width))
+    assert c.cin == 60 and c.cout == 19 and c.taps == 1
+    x = torch.randn(1, 57, 6, 5)
+    ref = bn(conv(x)).detach()[0].permute(1, 2, 0).reshape(30, 19)
+    xp = torch.full((30, 60), 1234.5)                          # garbage in the pad channels
+    xp[:, pos] = x[0].permute(1, 2, 0).reshape(30, 57)
+    prep = c.weights[0, 0]                                     # [cin padded to 8][20], output group 0
+    got = (xp @ prep[:60, :19]) * c.scale + c.shift
+    assert float((got - ref).abs().max()) < 1e-4 * float(ref.abs().max())
+    assert float(prep[[19, 39, 59]].abs().max()) == 0.0
+
+
+def test_average_pools_commute_with_the_1x1_convolution():
+    """VortexPooling (modules/model.py:114-135): W.pool^b(x) == pool^b(W.x) for AvgPool2d(3, 1, 1) with the zero
+    padding counted in the divisor -- the identity behind pooling 19 channels instead of 114."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 12, 10, 13, generator=g, dtype=torch.float64)
+    w = torch.randn(5, 12, 1, 1, generator=g, dtype=torch.float64)
+    pool = lambda t: F.avg_pool2d(t, 3, stride=1, padding=1, count_include_pad=True)     # noqa: E731
+    a, b = x, F.conv2d(x, w)
+    for _ in range(3):
+        a, b = pool(a), pool(b)
+        assert float((F.conv2d(a, w) - b).abs().max()) < 1e-13
