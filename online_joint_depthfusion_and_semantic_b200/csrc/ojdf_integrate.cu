@@ -448,7 +448,9 @@ finalize_kernel(Workspace ws, Volumes vol)
     for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
         const uint32_t slot = ws.list[seg0 + j];
         const uint4 entry = __ldcg(&ws.table[slot]);
-        if (entry.w > (uint32_t)kRankMax) continue;                      // handled by the cooperative blocks
+        // over-long voxels belong to the cooperative blocks, which may already have finalised the voxel and put
+        // its slot back to idle ({0,0,0,0}) by the time this block runs: never act on an idle slot
+        if (entry.x == 0u || entry.w > (uint32_t)kRankMax) continue;
         finalize_voxel(ws, vol, slot, entry);
     }
 }

@@ -44,9 +44,33 @@ CASES = [
     # role profile / timing experiments (flag 128 = per-role wait cycles of block 0; 16 = no MMAs, 32 = no split
     # work, 64 = 1xTF32, 1024 = busy-poll the A ring, 2048 = single accumulator set)
     ('P: dense', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 128 | 1),
-    ('P: dense no MMA no split', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 128 | 48 | 1),
+    ('P: dense no MMA', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 128 | 16 | 1),
+    ('P: dense no lo pass', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 128 | 32 | 1),
+    ('P: dense neither', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 128 | 48 | 1),
+    ('Q: dense', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 1),
+    ('Q: dense no MMA', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 16 | 1),
+    ('Q: dense neither', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 48 | 1),
+    ('Q: dense neither no B loads', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 48 | 256 | 1),
+    ('Q: dense neither no A loads', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 48 | 512 | 1),
+    ('Q: dense neither no loads', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 48 | 768 | 1),
+    ('Q: dense neither no loads per-thread stores', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 48 | 768 | 8 | 1),
+    ('Q: dense no B loads', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 256 | 1),
+    ('Q: dense no loads', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 768 | 1),
+    ('Q: 19->19', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 1),
+    ('Q: 19->19 no loads', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 768 | 1),
+    ('Q: 19->19 neither no loads', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 48 | 768 | 1),
+    ('P: dense MT=1', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 128 | 2 | 1),
+    ('P: dense per-tap boxes', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 128 | 4 | 1),
+    ('P: 19->19', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 128 | 1),
+    ('P: 19->19 no MMA', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 128 | 16 | 1),
     ('P: 456->114', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 1),
-    ('P: 456->114 no MMA no split', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 48 | 1),
+    ('P: 456->114 no MMA', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 16 | 1),
+    ('P: 456->114 neither', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 48 | 1),
+    ('P: 456->114 nacc 2', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 2048 | 1),
+    ('P: 19->114 x8', 240, 320, 19, 114, 1, 1, 20, 464, 116, 1, False, 8, 128 | 1),
+    ('P: 19->114 x8 no MMA', 240, 320, 19, 114, 1, 1, 20, 464, 116, 1, False, 8, 128 | 16 | 1),
+    ('P: 114->95', 240, 320, 114, 95, 1, 1, 116, 116, 0, 2, False, 1, 128 | 1),
+    ('P: dense (TS kernel)', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 65536 | 1),
 ]
 FN = 'ojdf_conv_tc_batched'
 
@@ -90,7 +114,7 @@ def run_case(idx, timing):
     st = torch.cuda.current_stream().cuda_stream
     scratch = torch.empty((64 << 20) // 4, dtype=torch.float32, device=dev)
     scratch_ptr, scratch_bytes = scratch.data_ptr(), scratch.numel() * 4
-    _lib.check(getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0xffff, scratch_ptr, scratch_bytes, st))
+    _lib.check(getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0x1ffff, scratch_ptr, scratch_bytes, st))
     torch.cuda.synchronize()
     worst = 0.0
     for y, out in zip(refs, outs):
@@ -105,10 +129,10 @@ def run_case(idx, timing):
     if timing:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(3):
-            getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0xffff, scratch_ptr, scratch_bytes, st)
+            getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0x1ffff, scratch_ptr, scratch_bytes, st)
         a.record()
         for _ in range(20):
-            getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0xffff, scratch_ptr, scratch_bytes, st)
+            getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0x1ffff, scratch_ptr, scratch_bytes, st)
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 20
@@ -116,15 +140,18 @@ def run_case(idx, timing):
     print(line, flush=True)
     if flags & 128:
         prof = (C.c_longlong * 32)()
-        L.ojdf_conv_tc_profile.argtypes = [C.c_void_p]
-        L.ojdf_conv_tc_profile(prof)                        # discard what the earlier launches accumulated
-        getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0xffff, scratch_ptr, scratch_bytes, st)
+        pf = L.ojdf_conv_tc_profile if (flags & 65536) else L.ojdf_conv_ss_profile
+        pf.argtypes = [C.c_void_p]
+        pf(prof)                                            # discard what the earlier launches accumulated
+        getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0x1ffff, scratch_ptr, scratch_bytes, st)
         torch.cuda.synchronize()
-        L.ojdf_conv_tc_profile(prof)
+        pf(prof)
         p = list(prof)
         print('   block 0 cycles: producer total %d (wait src_empty %d, b_empty %d) | mma total %d (acc_empty %d, b_full %d, a_full %d) | '
               'split0 total %d (src_full %d, a_empty %d) | split1 total %d (src_full %d, a_empty %d) | epilogue total %d (acc_full %d)'
               % (p[2], p[0], p[1], p[6], p[3], p[4], p[5], p[9], p[7], p[8], p[12], p[10], p[11], p[14], p[13]), flush=True)
+        if not (flags & 65536):
+            print('   ss issuer: in the MMA issue blocks %d, in the weight-stage commits %d' % (p[8], p[10]), flush=True)
 
 
 if __name__ == '__main__':
