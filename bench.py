@@ -20,10 +20,14 @@ rotated every frame so the voxel working set exceeds L2), no data-path collectiv
            against the measured dense bf16 tensor peak (sustained figure: the kernel is timed inside
            a long step); roofline_integrate / roofline_extract = algorithmic bytes (817 B per valid
            ray / 364 B per ray) / CUDA-event time of those calls, against the measured HBM peak
-  cpu_baseline = the CPU port of the same frame (oracle C for extract/integrate + the same
-           torch modules on CPU for the two networks) on a bounded sample, rank 0, N=1 only
+  cpu_baseline = the unmodified reference's Pipeline.fuse on the host CPU (kind "reference"; the CPU port --
+           oracle C for extract/integrate + the same torch modules on CPU -- is reported beside it as
+           cpu_baseline_port) on a bounded sample, rank 0, N=1 only
+  parity (--parity FRAMES) = F1 / mIoU / iou / acc of the CUDA path next to the CPU port after FRAMES frames
 
-Reference arm (--impl reference): that CPU port, timed on the host cores, same metric/config.
+Reference arm (--impl reference): the UNMODIFIED reference (git-ignored baseline/_ref, installed by
+baseline/install_ref.py; driven by baseline/harness.py) on the host cores, same metric/config; the CPU port only if
+that tree is missing.
 """
 import argparse
 import json
@@ -44,6 +48,9 @@ from online_joint_depthfusion_and_semantic_b200.config import fusion_config  # n
 from online_joint_depthfusion_and_semantic_b200.synthetic import SyntheticScene  # noqa: E402
 
 H, W, GRID, N_CLASSES = 240, 320, 256, 30
+# dram__bytes_read.sum + dram__bytes_write.sum per frame of each stage's kernels, from the committed `ncu --set full`
+# capture of this very command (profiles/r2_*; filled in after each kernel change, None = not captured for this build)
+TRAFFIC = {'fusionnet': None, 'integrate': None, 'extract': None}
 SCENES_PER_RANK, FRAMES_PER_SCENE = 4, 6
 METRIC = 'fused_frames_per_second_240x320_into_256cube'
 WORKLOAD = 'configs[1]: synthetic Replica-like room, 256^3 grid, 240x320 RGB-D, AdapNet++(stage2,30cls)+FusionNet_v3(sem)+extract+integrate'
@@ -122,11 +129,11 @@ class SceneSet:
 
 
 def build_world(device, rank, h=H, w=W, grid=GRID, scenes_per_rank=SCENES_PER_RANK, frames=FRAMES_PER_SCENE,
-                render_device=None):
+                render_device=None, strategy='predict'):
     from online_joint_depthfusion_and_semantic_b200.config import Config
     from online_joint_depthfusion_and_semantic_b200.modules.database import Database
     from online_joint_depthfusion_and_semantic_b200.modules.pipeline import Pipeline
-    cfg = fusion_config(h, w, semantics='class30', semantic_strategy='predict', use_semantics=True,
+    cfg = fusion_config(h, w, semantics='class30', semantic_strategy=strategy, use_semantics=True,
                         n_classes=N_CLASSES, stage=2, device=str(device))
     torch.manual_seed(1911)
     pipe = Pipeline(cfg)
@@ -174,8 +181,8 @@ class ResultTap:
         self.value = None
         inner = pipe._fusion
 
-        def tapped(inputs, values):
-            est = inner(inputs, values)
+        def tapped(inputs, values, **kw):
+            est = inner(inputs, values, **kw)
             self.value = est.abs().mean()
             return est
         pipe._fusion = tapped
@@ -253,8 +260,8 @@ def run_own(args):
     def stage(name):
         ev = timers.events.get(name, [])[-n_timed:]
         return float(np.mean([a.elapsed_time(b) for a, b in ev])) if ev else None
-    ext_ms, int_ms = stage('extract'), stage('integrate')
-    stages = {k: stage(k) for k in ('adapnet', 'extract', 'fusionnet', 'integrate')}
+    ext_ms, int_ms, plan_ms, rays_ms = stage('extract'), stage('integrate'), stage('integrate_plan') or 0.0, stage('rays') or 0.0
+    stages = {k: stage(k) for k in ('adapnet', 'rays', 'extract', 'fusionnet', 'integrate_plan', 'integrate')}
     # --- e2e: host frames, H2D + D2H inside the timed region
     ms_e2e = float('nan')
     if not args.skip_e2e:
@@ -271,27 +278,32 @@ def run_own(args):
     nv = float(np.mean([int((hb['mask'] & (hb['tof_depth'] != 0)).sum()) for hb in host_frames]))
     peak, tpeak, peak_src = peaks()
     int_bytes, ext_bytes = 817.0 * nv, 364.0 * n_rays
-    roof_int = {'kernel': 'ojdf_integrate (count + offsets + scatter + rank + finalize kernels)', 'bound': 'hbm',
-                'achieved': int_bytes / (int_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
-                'frac': int_bytes / (int_ms * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': int_bytes, 'ms_per_launch': float(int_ms)}
-    roof_ext = {'kernel': 'ojdf_extract (ray_setup_kernel + gather_kernel)', 'bound': 'hbm',
-                'achieved': ext_bytes / (ext_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
-                'frac': ext_bytes / (ext_ms * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': ext_bytes, 'ms_per_launch': float(ext_ms)}
+    int_total = int_ms + plan_ms
+    roof_int = {'kernel': 'ojdf_integrate_plan (count + offsets + scatter; side stream, overlaps the networks) + '
+                          'ojdf_integrate_apply (apply_short + apply_long; the only part after FusionNet)', 'bound': 'hbm',
+                'achieved': int_bytes / (int_total * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                'frac': int_bytes / (int_total * 1e-3) / 1e9 / peak, 'traffic': TRAFFIC.get('integrate'), 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': int_bytes, 'ms_per_launch': float(int_total),
+                'ms_plan_side_stream': float(plan_ms), 'ms_apply_critical_path': float(int_ms)}
+    ext_total = ext_ms + rays_ms
+    roof_ext = {'kernel': 'ojdf_rays + ojdf_gather (extract_kernel: per-ray records, then the fused gather that also writes '
+                          'FusionNet\'s input rows)', 'bound': 'hbm',
+                'achieved': ext_bytes / (ext_total * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                'frac': ext_bytes / (ext_total * 1e-3) / 1e9 / peak, 'traffic': TRAFFIC.get('extract'), 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': ext_bytes, 'ms_per_launch': float(ext_total)}
     fn_flop = 78.15e9 * (H * W) / 76800.0            # FusionNet_v3 (semantic head on), convolutions only, 2*MAC
     fn_ms = stages['fusionnet']
     roof_conv = {'kernel': 'tc::conv_tc_kernel (tcgen05 kind::tf32 tap GEMM, 3xTF32 split precision) over the FusionNet_v3 stack: '
                            '33 launches per frame + 13 small pooling / bias / packing launches inside the same bracket',
                  'bound': 'tensor', 'achieved': fn_flop / (fn_ms * 1e-3) / 1e12, 'peak': tpeak, 'unit': 'TFLOP/s',
-                 'frac': fn_flop / (fn_ms * 1e-3) / 1e12 / tpeak, 'traffic': None,
+                 'frac': fn_flop / (fn_ms * 1e-3) / 1e12 / tpeak, 'traffic': TRAFFIC.get('fusionnet'),
                  'peak_source': peak_src + ', dense bf16 sustained; the kernel issues 3 tf32 MMAs per algorithmic MAC '
                                            '(tf32 dense peak is half of bf16), so 1/6 of this peak is its arithmetic ceiling',
                  'algorithmic_flop_per_frame': fn_flop, 'ms_per_frame': float(fn_ms)} if fn_ms else None
     line = {
         'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64 ray geometry / f32 accumulation / f16+u8 volumes; FusionNet + AdapNet++ convolutions: fp32 via 3xTF32 tcgen05 (own kernels, ~1e-6 of fp32); AdapNet++ stem / 3 transposed convs: f32 library (TF32 off)',
+        'dtype': 'f64 ray geometry / f32 accumulation / f16+u8 volumes; FusionNet + AdapNet++ convolutions: fp32 via 3xTF32 tcgen05 (own kernels, ~1e-6 of fp32); AdapNet++ 7x7 stem + max-pool: f32 library (TF32 off)',
         'data': 'synthetic (analytic SDF room, seeded; random-init networks seed 1911)',
         'config': {'workload': WORKLOAD, 'frame': [H, W], 'grid': GRID, 'scenes_per_gpu': SCENES_PER_RANK,
                    'sharding': 'scenes one-per-rank, no collective',
@@ -302,7 +314,18 @@ def run_own(args):
         'stage_ms': stages,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line['cpu_baseline'] = cpu_port_fps(steps=3, warmup=1)
+        port = cpu_port_fps(steps=3, warmup=1)
+        ref = reference_fps(steps=3, warmup=1)
+        line['cpu_baseline'] = ref if ref is not None else port
+        line['cpu_baseline_port'] = port
+    if world == 1 and args.parity:
+        sys.path.insert(0, os.path.join(ROOT, 'tools'))
+        import parity_report
+        torch.cuda.empty_cache()
+        par = parity_report.parity(frames=args.parity, h=H, w=W, grid=GRID)
+        line['parity'] = {'frames': par['frames'], 'protocol': par['protocol'], 'cuda': par['cuda'], 'cpu_port': par['cpu_port'],
+                          'max_abs_diff_points': par['max_abs_diff_points'], 'volumes': par['volumes'],
+                          'within_half_point': bool(par['max_abs_diff_points'] <= 0.5)}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -359,19 +382,45 @@ def cpu_port_fps(steps, warmup, verbose=False):
             's_per_frame': dt / steps}
 
 
+def reference_fps(steps, warmup):
+    """The UNMODIFIED reference's own Pipeline.fuse (baseline/_ref, or /root/reference in the build container) on the host
+    CPU with every thread torch can use, in a child process (its `modules` / `utils` packages must not leak into this
+    one).  None if the reference tree is not there."""
+    from baseline import harness
+    if harness.ref_root() is None:
+        return None
+    cores = os.cpu_count() or 1
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'baseline', 'harness.py'), 'fps', '--frames', str(steps), '--h', str(H),
+                        '--w', str(W), '--grid', str(GRID), '--threads', str(cores)], capture_output=True, text=True, cwd=ROOT)
+    lines = [l for l in r.stdout.splitlines() if l.startswith('HARNESS_RESULT ')]
+    if r.returncode != 0 or not lines:
+        sys.stderr.write('bench.py: reference run failed, falling back to the CPU port\n' + r.stderr[-2000:] + '\n')
+        return None
+    d = json.loads(lines[-1][len('HARNESS_RESULT '):])
+    return {'value': d['fps'], 'unit': 'frames/s', 'cores': int(d['threads']), 'kind': 'reference',
+            'sample': '%d frames (after 1 warm-up) of the same workload on one scene through the unmodified reference '
+                      'Pipeline.fuse (modules/pipeline.py:173-248: AdapNet++ stage 2 + Extractor + FusionNet_v3 + Integrator) '
+                      'on torch-CPU, %d threads' % (d['frames'], d['threads']),
+            's_per_frame': d['s_per_frame']}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps = min(args.steps, 20)
-    warmup = min(args.warmup, 2)
-    r = cpu_port_fps(steps, warmup)
+    steps = min(args.steps, 8)                      # ~3.7 s per frame for the reference, ~0.7 s for the port
+    warmup = 1
+    r = reference_fps(steps, warmup)
+    if r is None:
+        steps = min(args.steps, 20)
+        r = cpu_port_fps(steps, min(args.warmup, 2))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': 'frames/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': warmup, 'ms_per_step': 1e3 * r['s_per_frame'], 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64/f32/f16 as the reference (CPU)', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'frame': [H, W], 'grid': GRID,
-                   'note': 'reference is pure Python/PyTorch and cannot travel to the GPU box; this is its CPU path restated '
+                   'note': 'kind "reference": the unmodified reference from git-ignored baseline/_ref (python baseline/install_ref.py) '
+                           'driven by baseline/harness.py; kind "port" (only if that tree is missing): its CPU path restated '
                            '(oracle C + identical torch CPU modules), pinned bit-exact to reference-generated fixtures'},
         'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
         'e2e': {'value': r['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -383,10 +432,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=60)
-    ap.add_argument('--warmup', type=int, default=6)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--parity', type=int, default=0, metavar='FRAMES',
+                    help='also fuse FRAMES frames through the CUDA path and the CPU port and report the metric parity (N=1)')
     ap.add_argument('--ncu-range', action='store_true', help='bracket the timed value-steps with cudaProfilerStart/Stop')
     ap.add_argument('--skip-e2e', action='store_true', help='(profiling runs only) skip the e2e leg')
     args = ap.parse_args()

@@ -77,6 +77,21 @@ int ojdf_extract(const float *depth_dev, const float *world_in_dev, int h, int w
                  float *out_vals_dev, float *out_wts_dev, float *out_world_dev, double *out_ray_dev,
                  double *out_points_dev, int64_t *out_idx_dev, double *out_w_dev, void *stream);
 
+/* The same step in two halves (the per-ray records depend only on depth and pose, so the pipeline computes them first
+ * and plans the integration with them while the networks run):
+ *   ojdf_rays   -- a5 + the record part of a6: world points (optional) and the (N,6) f64 per-ray records;
+ *   ojdf_gather -- a6-a8 from existing records, one kernel; optionally also writes FusionNet's pixel-major input
+ *                  rows [values(P) | weights(P) | last] (modules/pipeline.py:74-102) into pack_a_dev / pack_b_dev
+ *                  ((N, pack_stride) f32; last_*_dev (N) f32 = depth frame / normalised label frame; pack_b optional),
+ *                  which replaces a separate packing pass. */
+int ojdf_rays(const float *depth_dev, const float *world_in_dev, int h, int w, const float *Kinv_host,
+              const float *E_host, const double *origin_host, double resolution, float *out_world_dev,
+              double *out_ray_dev, void *stream);
+int ojdf_gather(const double *ray_dev, int h, int w, const void *tsdf_dev, const void *wvol_dev, int X, int Y, int Z,
+                int P, float *out_vals_dev, float *out_wts_dev, double *out_points_dev, int64_t *out_idx_dev,
+                double *out_w_dev, float *pack_a_dev, float *pack_b_dev, const float *last_a_dev,
+                const float *last_b_dev, int pack_stride, void *stream);
+
 /* Bytes of scratch ojdf_integrate*() needs for up to `max_entries` (ray,sample,corner)
  * entries per call: N*tail*8 for the frame form, M1*8 for the updates form. */
 size_t ojdf_integrate_workspace_bytes(int64_t max_entries);
@@ -107,6 +122,22 @@ int ojdf_integrate(const double *ray_dev, const float *filt_depth_dev, const flo
                    const uint8_t *pix_ids_dev, const float *pix_scores_dev,
                    uint8_t *ids_vol_dev, void *scores_vol_dev, int do_semantics,
                    void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* The same step in two halves, so that the part that does not need the network can leave the critical path:
+ *   ojdf_integrate_plan  -- needs only geometry (per-ray records + masked depth): groups the frame's entries by voxel
+ *                           into the workspace.  Independent of FusionNet / AdapNet++: the pipeline issues it on a side
+ *                           stream right after the per-ray records exist, while the networks run;
+ *   ojdf_integrate_apply -- the network output, labels and scores are gathered per entry, each voxel's entries are
+ *                           visited in ascending order and the volumes are updated; the workspace returns to idle.
+ * ojdf_integrate == plan followed by apply on one stream.  Between the two calls the workspace must not be used by
+ * another frame; arguments N, P, tail, X, Y, Z must be the same in both. */
+int ojdf_integrate_plan(const double *ray_dev, const float *filt_depth_dev, int64_t N, int P, int tail,
+                        int X, int Y, int Z, void *workspace_dev, size_t workspace_bytes, void *stream);
+int ojdf_integrate_apply(const float *est_dev, int64_t N, int P, int tail, float clamp_value,
+                         void *tsdf_dev, void *wvol_dev, int X, int Y, int Z,
+                         const uint8_t *pix_ids_dev, const float *pix_scores_dev,
+                         uint8_t *ids_vol_dev, void *scores_vol_dev, int do_semantics,
+                         void *workspace_dev, size_t workspace_bytes, void *stream);
 
 /* ---- a14/a15 in the reference's own `updates` form (modules/integrator.py:15-126) ------
  *   values_dev (M1) f32 already clamped, idx_dev (M1,8,3) i64, w_dev (M1,8) f64,

@@ -21,11 +21,15 @@ _SIGNATURES = {
     'ojdf_unproject': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     'ojdf_extract': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _d, _vp, _vp, _i, _i, _i, _i,
                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'ojdf_rays': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _d, _vp, _vp, _vp]),
+    'ojdf_gather': (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     'ojdf_integrate_workspace_bytes': (_sz, [_i64]),
     'ojdf_integrate_workspace_init': (_i, [_vp, _sz, _vp]),
     'ojdf_integrate_workspace_idle_bytes': (_sz, [_sz]),
     'ojdf_integrate': (_i, [_vp, _vp, _vp, _i64, _i, _i, _f, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i,
                             _vp, _sz, _vp]),
+    'ojdf_integrate_plan': (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    'ojdf_integrate_apply': (_i, [_vp, _i64, _i, _i, _f, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     'ojdf_integrate_updates': (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i,
                                     _vp, _sz, _vp]),
     'ojdf_conv_nhwc': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _i, _i, _vp]),

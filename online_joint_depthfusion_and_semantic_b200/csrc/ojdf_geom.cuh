@@ -82,8 +82,12 @@ __device__ __forceinline__ Axis axis_setup(double p)
     const double nb = (double)((df > 0.0) - (df < 0.0));       // torch.sign
     ax.a = fabs(__dsub_rn(p, ctr));
     ax.ai = __dsub_rn(1.0, ax.a);
-    ax.i0 = (long long)fl;
-    ax.i1 = (long long)__dadd_rn(fl, nb);
+    // double -> int64 of a non-finite value: the reference's CPU conversion yields INT64_MIN (so the corner fails
+    // get_index_mask and is dropped, modules/extractor.py:596-607), CUDA's yields 0 for NaN -- an in-grid voxel that a
+    // NaN depth pixel would then poison.  Reproduce the CPU result.
+    const bool fin = isfinite(fl);
+    ax.i0 = fin ? (long long)fl : (long long)0x8000000000000000ull;
+    ax.i1 = fin ? (long long)__dadd_rn(fl, nb) : (long long)0x8000000000000000ull;
     return ax;
 }
 

@@ -3,30 +3,28 @@
 // The reference sums, per voxel, the contributions w and w*v of every (ray,sample,corner)
 // entry that lands in it, in ascending entry order e (CPU index_add_ order),
 // in fp32.  fp32 addition is not associative and the result is stored as fp16, so bit-exact
-// parity needs exactly that order.  The kernels below do a counting sort of the entries by voxel
-// and then RANK every entry inside its voxel -- no floating-point atomics, no G^3 scratch, no
-// global sort, no serial per-voxel sort:
+// parity needs exactly that order.  The work is split in two:
 //
+// PLAN (needs only the geometry: per-ray records + depth mask -- independent of the network, so the pipeline builds
+// it on a side stream while AdapNet++ / FusionNet run):
 //   count    : one thread per (ray,sample): recompute the 8 corners from the extractor's per-ray
 //              record, find/claim the voxel's slot in an open-addressing hash (key = linear voxel
 //              index) and take an arrival number from its counter; slot and arrival number are
 //              remembered per entry (coalesced 64 B/thread).  The thread that claims a voxel
 //              appends the slot to its block's touched list.
 //   offsets  : one thread per touched voxel: block scan of the counts + one atomic per block gives
-//              every voxel a contiguous segment {off, len}; voxels longer than kRankMax are queued.
+//              every voxel a contiguous segment {off, len}; voxels with more than 32 entries are queued.
 //   scatter  : one thread per (ray,sample): write e to arrival[off + arrival number].
-//   rank     : one thread per (ray,sample): for each of its entries count the entries of the same
-//              voxel with a smaller e (a dense, independent, cache-friendly loop over the voxel's
-//              arrival segment) and store the record {e, w, w*v, label} at sorted[off + rank].
-//              Entries of over-long voxels are stored unsorted instead and a whole block sorts
-//              that segment in place with an all-ascending bitonic network.
-//   finalize : one thread per touched voxel streams its sorted segment: fp32 sums in ascending e,
-//              the running-mean update with fp16 round-to-nearest stores (integrator.py:77-88),
-//              the semantic "highest entry wins" update (integrator.py:90-124, App. A.5), and the
-//              slot goes back to idle.
+//   rank     : one thread per (ray,sample): for each of its entries count the entries of the same voxel with a smaller e
+//              and store {e, w} at sorted[off + rank]; over-long voxels (> 2048 entries) are left for a block sort.
+// APPLY (the only part after the network; one kernel):
+//   apply    : one thread per touched voxel streams its sorted segment; the network value / label of every entry is
+//              gathered by e: fp32 sums in ascending e, the running-mean update with fp16 round-to-nearest stores
+//              (integrator.py:77-88), the semantic "highest entry wins" update (integrator.py:90-124, App. A.5), and
+//              the slot goes back to idle.  Over-long voxels: a block sorts the segment first.
 //
-// The result is deterministic and bit-identical to the single-threaded reference for every list
-// length (near-camera frames put >10^4 entries into one voxel; see tests).
+// No floating-point atomics, no G^3 scratch, no global sort.  The result is deterministic and bit-identical to the
+// single-threaded reference for every list length (near-camera frames put >10^4 entries into one voxel; see tests).
 #include "ojdf_internal.h"
 
 namespace ojdf {
@@ -35,7 +33,7 @@ constexpr int kThreads = 256;
 constexpr int kSegment = kThreads * 8;        // entries per block == max voxels a block can claim
 constexpr int kRankMax = 2048;                // longest per-voxel list ranked by counting; above: block sort
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
-constexpr int kCoopBlocks = 148;              // persistent blocks draining the long-voxel queue
+constexpr int kCoopBlocks = 148;              // blocks draining the long-voxel queue
 
 struct Workspace {
     uint4 *table;          // {key + 1 (0 = empty), arrival counter, segment offset, segment length}; zero when idle
@@ -43,7 +41,7 @@ struct Workspace {
     uint32_t *earr;        // arrival number of every entry inside its voxel
     uint32_t *list;        // touched slots, per-block segments of kSegment
     uint32_t *arrival;     // e of every entry, grouped by voxel, arrival order
-    uint4 *sorted;         // {e, w bits, (w*v) bits, label} records, grouped by voxel, ascending e
+    uint2 *sorted;         // {e, weight bits} records, grouped by voxel, ascending e
     uint32_t *queue;       // slots of voxels with more than kRankMax entries
     uint32_t *count;       // touched voxels per block
     uint32_t *ctrl;        // [0] segment bump cursor, [1] queue length; zero when idle
@@ -75,7 +73,7 @@ static size_t carve(Workspace &ws, void *base, long long cap)
     ws.earr = (uint32_t *)take(4 * (size_t)cap);
     ws.list = (uint32_t *)take(4 * (size_t)blocks * kSegment);
     ws.arrival = (uint32_t *)take(4 * (size_t)cap);
-    ws.sorted = (uint4 *)take(16 * (size_t)cap);
+    ws.sorted = (uint2 *)take(8 * (size_t)cap);
     ws.queue = (uint32_t *)take(4 * ((size_t)cap / kRankMax + 1));
     ws.count = (uint32_t *)take(4 * (size_t)blocks);
     ws.log2_slots = l;
@@ -167,11 +165,10 @@ __device__ __forceinline__ bool load_sample(const Source &src, long long t, Samp
         const int k = (int)(t - n * src.T);
         if (!(src.filt[n] != 0.0f)) return false;                       // modules/pipeline.py:143-146
         sample_corners(src.ray, n, k - src.P / 2, src.X, src.Y, src.Z, s);
-        const float v = src.est[n * src.P + k], c = src.clampv;
-        val = v < -c ? -c : (v > c ? c : v);                             // torch.clamp, pipeline.py:157-159
+        val = 0.0f;                                                      // the plan kernels never look at the values
     } else {
         sample_updates(src.idx, src.wts, t, src.X, src.Y, src.Z, s);
-        val = src.values[t];
+        val = 0.0f;
     }
     return true;
 }
@@ -324,15 +321,18 @@ scatter_kernel(long long items, Workspace ws)
         if (slot[c] != kNoSlot) ws.arrival[off[c] + arr[c]] = (uint32_t)(t * 8 + c);
 }
 
+// One thread per (ray,sample): for each of its entries count the entries of the same voxel with a smaller e (a dense,
+// independent, cache-friendly loop over the voxel's arrival segment) and store {e, weight} at sorted[off + rank].
+// Entries of over-long voxels keep their arrival position; a whole block sorts that segment later.  Needs only the
+// geometry, so it belongs to the plan.
 template <bool FRAME>
 __global__ void __launch_bounds__(kThreads)
-rank_kernel(Source src, Workspace ws, const uint8_t *__restrict__ sem_ids)
+rank_kernel(Source src, Workspace ws)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     Sample s;
     float val;
     if (!load_sample<FRAME>(src, t, s, val)) return;
-    const uint32_t label = sem_ids ? (uint32_t)sem_ids[FRAME ? t / src.T : t] : 0u;   // the sample's label rides in the record
     uint32_t slot[8], arr[8];
     load8(ws.eslot + t * 8, slot);
     load8(ws.earr + t * 8, arr);
@@ -354,21 +354,63 @@ rank_kernel(Source src, Workspace ws, const uint8_t *__restrict__ sem_ids)
             for (; q < len; ++q) r0 += a[q] < e;
             r = (r0 + r1) + (r2 + r3);
         }
-        const float u = __fmul_rn(s.w[c], val);                          // integrator.py:55, separately rounded
-        ws.sorted[off + r] = make_uint4(e, __float_as_uint(s.w[c]), __float_as_uint(u), label);
+        ws.sorted[off + r] = make_uint2(e, __float_as_uint(s.w[c]));
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-struct Volumes {
+// The second half: everything that needs the network output.  `est` / labels / scores are gathered per entry from
+// the entry number e (frame form: ray n = e / (8 T), sample k = (e / 8) % T; updates form: record e / 8).
+struct Apply {
     __half *tsdf; __half *wvol; uint8_t *ids; __half *scores;
-    const uint8_t *sem_ids; const float *sem_scores;   // per record: entry e belongs to record e / sem_div
-    uint32_t sem_div; int do_sem;
+    const float *est;              // frame form: (N, P) network output; updates form: (M1) values
+    const uint8_t *sem_ids; const float *sem_scores;
+    uint32_t T8;                   // frame form: 8 * tail; updates form: 8
+    int P, frame, do_sem;
+    float clampv;
 };
+
+__device__ __forceinline__ float entry_value(const Apply &a, uint32_t e)
+{
+    if (!a.frame) return a.est[e >> 3];
+    const uint32_t n = e / a.T8, k = (e - n * a.T8) >> 3;
+    const float v = a.est[(size_t)n * a.P + k], c = a.clampv;
+    return v < -c ? -c : (v > c ? c : v);                                  // torch.clamp, pipeline.py:157-159
+}
+__device__ __forceinline__ uint32_t entry_record(const Apply &a, uint32_t e) { return a.frame ? e / a.T8 : e >> 3; }
+
+// Running state of one voxel while its entries are visited in ascending e (integrator.py:55-124, App. A.4-A.5).
+struct VoxelAcc {
+    float W, U;
+    uint32_t e_last, e_label;
+    __device__ __forceinline__ void init() { W = 0.0f; U = 0.0f; e_last = 0; e_label = kNoSlot; }
+    __device__ __forceinline__ void add(float w, float u, uint32_t e, bool label_differs)
+    {
+        W = __fadd_rn(W, w);                                                // index_add_, ascending e (integrator.py:60,65)
+        U = __fadd_rn(U, u);
+        e_last = e;
+        if (label_differs) e_label = e;
+    }
+};
+
+__device__ __forceinline__ void store_voxel(const Apply &a, uint32_t key, const VoxelAcc &v, float wo, float vo, uint8_t id_old, float sc_old)
+{
+    const float wn = __fadd_rn(wo, v.W);
+    a.wvol[key] = __float2half_rn(wn);                                                        // integrator.py:77-78
+    a.tsdf[key] = __float2half_rn(__fdiv_rn(__fadd_rn(__fmul_rn(wo, vo), v.U), wn));          // integrator.py:82-83 (0/0 -> NaN kept)
+    if (a.do_sem) {
+        const float s_last = a.sem_scores[entry_record(a, v.e_last)];                         // highest entry wins
+        a.scores[key] = __float2half_rn(s_last > sc_old ? s_last : sc_old);                   // integrator.py:112-113,124
+        if (v.e_label != kNoSlot) {                                                           // some entry's label differs
+            const uint32_t r = entry_record(a, v.e_label);
+            a.ids[key] = a.sem_scores[r] > sc_old ? a.sem_ids[r] : id_old;                     // integrator.py:115-116,123
+        }
+    }
+}
 
 // All-ascending bitonic network over seg[0..len): comparators whose upper index is >= len are
 // no-ops (virtual +inf padding), so any length sorts in place.
-__device__ __forceinline__ void block_sort(uint4 *seg, uint32_t len)
+__device__ __forceinline__ void block_sort(uint2 *seg, uint32_t len)
 {
     uint32_t P = 1;
     while (P < len) P <<= 1;
@@ -376,8 +418,8 @@ __device__ __forceinline__ void block_sort(uint4 *seg, uint32_t len)
         for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {        // mirror step: i <-> i ^ (k-1)
             const uint32_t j = i ^ (k - 1);
             if (j > i && j < len) {
-                const uint4 a = seg[i], b = seg[j];
-                if (a.x > b.x) { seg[i] = b; seg[j] = a; }
+                const uint2 x = seg[i], y = seg[j];
+                if (x.x > y.x) { seg[i] = y; seg[j] = x; }
             }
         }
         __syncthreads();
@@ -385,8 +427,8 @@ __device__ __forceinline__ void block_sort(uint4 *seg, uint32_t len)
             for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
                 const uint32_t j = i ^ s;
                 if (j > i && j < len) {
-                    const uint4 a = seg[i], b = seg[j];
-                    if (a.x > b.x) { seg[i] = b; seg[j] = a; }
+                    const uint2 x = seg[i], y = seg[j];
+                    if (x.x > y.x) { seg[i] = y; seg[j] = x; }
                 }
             }
             __syncthreads();
@@ -394,42 +436,47 @@ __device__ __forceinline__ void block_sort(uint4 *seg, uint32_t len)
     }
 }
 
-// One thread: stream the sorted segment of the voxel in `slot`, update the volumes, free the slot.
-__device__ __forceinline__ void finalize_voxel(const Workspace &ws, const Volumes &v, uint32_t slot, const uint4 entry)
+// One thread: visit the sorted segment of the voxel in `slot` (4 records and their gathers in flight at a time),
+// update the volumes, free the slot.
+__device__ __forceinline__ void apply_voxel(const Workspace &ws, const Apply &a, uint32_t slot, const uint4 entry)
 {
     const uint32_t key = entry.x - 1u, off = entry.z, len = entry.w;
     ws.table[slot] = make_uint4(0u, 0u, 0u, 0u);                        // slot back to idle for the next frame
     uint8_t id_old = 0;
     float sc_old = 0.0f;
-    if (v.do_sem) { id_old = v.ids[key]; sc_old = __half2float(v.scores[key]); }
-    const float wo = __half2float(v.wvol[key]), vo = __half2float(v.tsdf[key]);
-    float W = 0.0f, U = 0.0f;
-    uint32_t e_last = 0, e_label = kNoSlot;
-    const uint4 *seg = ws.sorted + off;
-    for (uint32_t q = 0; q < len; ++q) {
-        const uint4 r = seg[q];
-        W = __fadd_rn(W, __uint_as_float(r.y));                          // index_add_, ascending e (integrator.py:60,65)
-        U = __fadd_rn(U, __uint_as_float(r.z));
-        e_last = r.x;
-        if (r.w != (uint32_t)id_old) e_label = r.x;                      // only read when do_sem
-    }
-    const float wn = __fadd_rn(wo, W);
-    v.wvol[key] = __float2half_rn(wn);                                                        // integrator.py:77-78
-    v.tsdf[key] = __float2half_rn(__fdiv_rn(__fadd_rn(__fmul_rn(wo, vo), U), wn));           // integrator.py:82-83 (0/0 -> NaN kept)
-    if (v.do_sem) {
-        const float s_last = v.sem_scores[e_last / v.sem_div];                                // highest entry wins
-        v.scores[key] = __float2half_rn(s_last > sc_old ? s_last : sc_old);                   // integrator.py:112-113,124
-        if (e_label != kNoSlot) {                                                             // some entry's label differs
-            const uint32_t r = e_label / v.sem_div;
-            v.ids[key] = v.sem_scores[r] > sc_old ? v.sem_ids[r] : id_old;                     // integrator.py:115-116,123
+    if (a.do_sem) { id_old = a.ids[key]; sc_old = __half2float(a.scores[key]); }
+    const float wo = __half2float(a.wvol[key]), vo = __half2float(a.tsdf[key]);
+    VoxelAcc acc;
+    acc.init();
+    const uint2 *seg = ws.sorted + off;
+    uint32_t q = 0;
+    for (; q + 4 <= len; q += 4) {
+        uint2 r[4];
+        float u[4];
+        uint32_t lab[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = seg[q + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            u[i] = __fmul_rn(__uint_as_float(r[i].y), entry_value(a, r[i].x));      // integrator.py:55, separately rounded
+            lab[i] = a.do_sem ? (uint32_t)a.sem_ids[entry_record(a, r[i].x)] : 0u;
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc.add(__uint_as_float(r[i].y), u[i], r[i].x, a.do_sem && lab[i] != (uint32_t)id_old);
     }
+    for (; q < len; ++q) {
+        const uint2 r = seg[q];
+        const float w = __uint_as_float(r.y);
+        const bool differs = a.do_sem && (uint32_t)a.sem_ids[entry_record(a, r.x)] != (uint32_t)id_old;
+        acc.add(w, __fmul_rn(w, entry_value(a, r.x)), r.x, differs);
+    }
+    store_voxel(a, key, acc, wo, vo, id_old, sc_old);
 }
 
-// grid = kCoopBlocks persistent blocks that sort + finalize the over-long voxels (scheduled first:
-// they are the long poles) followed by one block per count block (one thread per touched voxel).
+// grid = kCoopBlocks blocks that sort + apply the over-long voxels (scheduled first: they are the long poles) followed
+// by one block per count block (one thread per touched voxel).
 __global__ void __launch_bounds__(kThreads)
-finalize_kernel(Workspace ws, Volumes vol)
+apply_kernel(Workspace ws, Apply a)
 {
     if (blockIdx.x < (uint32_t)kCoopBlocks) {
         const uint32_t nq = ws.ctrl[1];
@@ -437,7 +484,7 @@ finalize_kernel(Workspace ws, Volumes vol)
             const uint32_t slot = ws.queue[q];
             const uint4 entry = ws.table[slot];
             block_sort(ws.sorted + entry.z, entry.w);
-            if (threadIdx.x == 0) finalize_voxel(ws, vol, slot, entry);
+            if (threadIdx.x == 0) apply_voxel(ws, a, slot, entry);
             __syncthreads();
         }
         return;
@@ -448,27 +495,34 @@ finalize_kernel(Workspace ws, Volumes vol)
     for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
         const uint32_t slot = ws.list[seg0 + j];
         const uint4 entry = __ldcg(&ws.table[slot]);
-        // over-long voxels belong to the cooperative blocks, which may already have finalised the voxel and put
-        // its slot back to idle ({0,0,0,0}) by the time this block runs: never act on an idle slot
+        // over-long voxels belong to the cooperative blocks, which may already have applied the voxel and put its slot
+        // back to idle ({0,0,0,0}) by the time this block runs: never act on an idle slot
         if (entry.x == 0u || entry.w > (uint32_t)kRankMax) continue;
-        finalize_voxel(ws, vol, slot, entry);
+        apply_voxel(ws, a, slot, entry);
     }
 }
 
-// Runs after finalize (stream order): control words back to idle.
+// Runs after the apply kernel (stream order): control words back to idle.
 __global__ void reset_ctrl_kernel(Workspace ws) { if (threadIdx.x < 4) ws.ctrl[threadIdx.x] = 0u; }
 
+// Plan: everything that only needs the geometry (per-ray records + mask, or the updates' indices / weights).
 template <bool FRAME>
-static int run(const Source &src, const Volumes &vol, Workspace &ws, cudaStream_t s)
+static int run_plan(const Source &src, Workspace &ws, cudaStream_t s)
 {
     const unsigned blocks = (unsigned)((src.items + kThreads - 1) / kThreads);
     count_kernel<FRAME><<<blocks, kThreads, 0, s>>>(src, ws);
     offsets_kernel<<<blocks, kThreads, 0, s>>>(ws);
     scatter_kernel<<<blocks, kThreads, 0, s>>>(src.items, ws);
-    rank_kernel<FRAME><<<blocks, kThreads, 0, s>>>(src, ws, vol.do_sem ? vol.sem_ids : nullptr);
-    finalize_kernel<<<blocks + kCoopBlocks, kThreads, 0, s>>>(ws, vol);
+    rank_kernel<FRAME><<<blocks, kThreads, 0, s>>>(src, ws);
+    return launched(4);
+}
+
+static int run_apply(long long items, const Apply &a, Workspace &ws, cudaStream_t s)
+{
+    const unsigned blocks = (unsigned)((items + kThreads - 1) / kThreads);
+    apply_kernel<<<blocks + kCoopBlocks, kThreads, 0, s>>>(ws, a);
     reset_ctrl_kernel<<<1, 32, 0, s>>>(ws);
-    return launched(6);
+    return launched(2);
 }
 
 }  // namespace ojdf
@@ -507,14 +561,32 @@ static int check_common(const void *tsdf, const void *wvol, int X, int Y, int Z,
     return 0;
 }
 
-extern "C" int ojdf_integrate(const double *ray_dev, const float *filt_depth_dev, const float *est_dev, int64_t N,
-                              int P, int tail, float clamp_value, void *tsdf_dev, void *wvol_dev, int X, int Y, int Z,
-                              const uint8_t *pix_ids_dev, const float *pix_scores_dev, uint8_t *ids_vol_dev,
-                              void *scores_vol_dev, int do_semantics, void *workspace_dev, size_t workspace_bytes,
-                              void *stream)
+static int frame_args_ok(int64_t N, int P, int tail)
 {
-    if (!ray_dev || !filt_depth_dev || !est_dev || N < 0 || P < 1 || P > 33 || !(P & 1) || tail < 1 || tail > P)
-        return OJDF_ERR_BADARG;
+    return !(N < 0 || P < 1 || P > 33 || !(P & 1) || tail < 1 || tail > P);
+}
+
+extern "C" int ojdf_integrate_plan(const double *ray_dev, const float *filt_depth_dev, int64_t N, int P, int tail,
+                                   int X, int Y, int Z, void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    if (!ray_dev || !filt_depth_dev || !frame_args_ok(N, P, tail) || X <= 0 || Y <= 0 || Z <= 0) return OJDF_ERR_BADARG;
+    if (!workspace_dev) return OJDF_ERR_WORKSPACE;
+    const long long NT = (long long)N * tail, entries = NT * 8;
+    if ((long long)X * Y * Z >= 0xFFFFFFFFll || entries >= 0x7FFFFFFFll - kSegment) return OJDF_ERR_TOOLARGE;
+    if (N == 0) return 0;
+    Workspace ws;
+    int rc;
+    if ((rc = bind_workspace(ws, workspace_dev, workspace_bytes, entries)) != 0) return rc;
+    Source src = {ray_dev, filt_depth_dev, nullptr, nullptr, nullptr, nullptr, NT, P, tail, 0.0f, X, Y, Z};
+    return run_plan<true>(src, ws, (cudaStream_t)stream);
+}
+
+extern "C" int ojdf_integrate_apply(const float *est_dev, int64_t N, int P, int tail, float clamp_value, void *tsdf_dev,
+                                    void *wvol_dev, int X, int Y, int Z, const uint8_t *pix_ids_dev,
+                                    const float *pix_scores_dev, uint8_t *ids_vol_dev, void *scores_vol_dev,
+                                    int do_semantics, void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    if (!est_dev || !frame_args_ok(N, P, tail)) return OJDF_ERR_BADARG;
     const long long NT = (long long)N * tail, entries = NT * 8;
     int rc = check_common(tsdf_dev, wvol_dev, X, Y, Z, pix_ids_dev, pix_scores_dev, ids_vol_dev, scores_vol_dev,
                           do_semantics, workspace_dev, entries);
@@ -522,10 +594,22 @@ extern "C" int ojdf_integrate(const double *ray_dev, const float *filt_depth_dev
     if (N == 0) return 0;
     Workspace ws;
     if ((rc = bind_workspace(ws, workspace_dev, workspace_bytes, entries)) != 0) return rc;
-    Source src = {ray_dev, filt_depth_dev, est_dev, nullptr, nullptr, nullptr, NT, P, tail, clamp_value, X, Y, Z};
-    Volumes vol = {(__half *)tsdf_dev, (__half *)wvol_dev, ids_vol_dev, (__half *)scores_vol_dev,
-                   pix_ids_dev, pix_scores_dev, (uint32_t)tail * 8u, do_semantics};
-    return run<true>(src, vol, ws, (cudaStream_t)stream);
+    Apply a = {(__half *)tsdf_dev, (__half *)wvol_dev, ids_vol_dev, (__half *)scores_vol_dev, est_dev, pix_ids_dev,
+               pix_scores_dev, (uint32_t)tail * 8u, P, 1, do_semantics, clamp_value};
+    return run_apply(NT, a, ws, (cudaStream_t)stream);
+}
+
+extern "C" int ojdf_integrate(const double *ray_dev, const float *filt_depth_dev, const float *est_dev, int64_t N,
+                              int P, int tail, float clamp_value, void *tsdf_dev, void *wvol_dev, int X, int Y, int Z,
+                              const uint8_t *pix_ids_dev, const float *pix_scores_dev, uint8_t *ids_vol_dev,
+                              void *scores_vol_dev, int do_semantics, void *workspace_dev, size_t workspace_bytes,
+                              void *stream)
+{
+    if (!est_dev || !tsdf_dev || !wvol_dev) return OJDF_ERR_BADARG;
+    int rc = ojdf_integrate_plan(ray_dev, filt_depth_dev, N, P, tail, X, Y, Z, workspace_dev, workspace_bytes, stream);
+    if (rc) return rc;
+    return ojdf_integrate_apply(est_dev, N, P, tail, clamp_value, tsdf_dev, wvol_dev, X, Y, Z, pix_ids_dev, pix_scores_dev,
+                                ids_vol_dev, scores_vol_dev, do_semantics, workspace_dev, workspace_bytes, stream);
 }
 
 extern "C" int ojdf_integrate_updates(const float *values_dev, const int64_t *idx_dev, const double *w_dev, int64_t M1,
@@ -542,7 +626,8 @@ extern "C" int ojdf_integrate_updates(const float *values_dev, const int64_t *id
     Workspace ws;
     if ((rc = bind_workspace(ws, workspace_dev, workspace_bytes, entries)) != 0) return rc;
     Source src = {nullptr, nullptr, nullptr, values_dev, (const long long *)idx_dev, w_dev, M1, 0, 0, 0.0f, X, Y, Z};
-    Volumes vol = {(__half *)tsdf_dev, (__half *)wvol_dev, ids_vol_dev, (__half *)scores_vol_dev,
-                   ids_dev, scores_dev, 8u, do_semantics};
-    return run<false>(src, vol, ws, (cudaStream_t)stream);
+    if ((rc = run_plan<false>(src, ws, (cudaStream_t)stream)) != 0) return rc;
+    Apply a = {(__half *)tsdf_dev, (__half *)wvol_dev, ids_vol_dev, (__half *)scores_vol_dev, values_dev, ids_dev, scores_dev,
+               8u, 0, 0, do_semantics, 0.0f};
+    return run_apply(M1, a, ws, (cudaStream_t)stream);
 }

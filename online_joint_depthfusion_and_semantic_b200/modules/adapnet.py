@@ -23,6 +23,8 @@ from torch import nn
 from torch.nn import functional as F
 from torchvision.models import resnet50
 
+from ._engine_cache import EngineOwner
+
 
 class BottleneckSSMA(nn.Module):
     """Multi-scale residual unit.  (in_channels, out_channels, r1, r2, d3) as in the reference."""
@@ -186,7 +188,7 @@ class SSMA(nn.Module):
         return self.final_conv(x * self.link(x))
 
 
-class AdapNet(nn.Module):
+class AdapNet(EngineOwner, nn.Module):
     def __init__(self, config):
         super().__init__()
         self.stage = config.stage
@@ -222,16 +224,20 @@ class AdapNet(nn.Module):
         self._engine = None
         self._full_engine = None
 
+    def engine_token(self):
+        """Identity of the launch plans a CUDA graph captured over this module points into (Pipeline._segmentation)."""
+        return (self._engine, self._full_engine)
+
     def train(self, mode=True):
-        self._drop_engines()
+        self._invalidate()
         return super().train(mode)
 
     def _apply(self, fn, *a, **k):
-        self._drop_engines()
+        self._invalidate()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._drop_engines()
+        self._invalidate()
         return super().load_state_dict(*a, **k)
 
     def engine_ready(self, x):
@@ -240,6 +246,8 @@ class AdapNet(nn.Module):
     def _tail(self, pres):
         from .adapnet_engine import EncoderTailEngine
         h, w = pres[0].shape[-2:]
+        self._hook_load_state_dict()
+        self.engines_current()
         e = self._engine
         if e is None or (e.h, e.w) != (h, w) or e.device != pres[0].device:
             encs = [self.encoder_mod1] + ([self.encoder_mod2] if self.stage != 1 else [])
@@ -258,6 +266,8 @@ class AdapNet(nn.Module):
     def _whole(self, mod1, mod2):
         from .adapnet_engine import AdapNetEngine
         h, w = mod1.shape[-2:]
+        self._hook_load_state_dict()
+        self.engines_current()
         e = self._full_engine
         if e is None or (e.h, e.w) != (h, w) or e.device != mod1.device:
             e = self._full_engine = AdapNetEngine(self, h, w, mod1.device)

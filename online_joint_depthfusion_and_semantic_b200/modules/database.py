@@ -17,6 +17,11 @@ import torch
 from . import metrics
 
 
+def _np(x):
+    """numpy view of a tensor (device -> host copy) or of an array."""
+    return x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)
+
+
 class Voxelgrid:
     """The four attributes of deps/graphics Voxelgrid the hot path touches (voxelgrid.py:54-70,157-161)."""
 
@@ -96,17 +101,60 @@ class Database:
                 self.ids_est[s].volume = torch.zeros(shape, dtype=torch.uint8, device=self.device)
                 self.scores[s].volume = torch.zeros(shape, dtype=torch.float16, device=self.device)
 
+    # ---- host <-> device round trip (modules/database.py:383-421).  The reference's drivers call to_numpy() before the
+    # filters / metrics (test_fusion.py:82, train_fusion.py:198,215) and to_torch() before fusing again
+    # (train_fusion.py:254).  Here the filters and metrics run on the device either way: they accept whatever form the
+    # volumes are in and leave them in that form.
+    def to_numpy(self):
+        for s in self.scenes:
+            self.origin[s] = _np(self.origin[s])
+            self.scenes_est[s].volume = _np(self.scenes_est[s].volume)
+            self.scenes_gt[s].volume = _np(self.scenes_gt[s].volume)
+            self.fusion_weights[s] = _np(self.fusion_weights[s])
+            if self.semantics:
+                self.ids_est[s].volume = _np(self.ids_est[s].volume)
+                self.scores[s].volume = _np(self.scores[s].volume)
+                if self.semantic_grid:
+                    self.ids_gt[s].volume = _np(self.ids_gt[s].volume)
+
+    def to_torch(self, gt=True, scenes=None):
+        """Back to device tensors (every volume lives on `self.device`: the `efficient` implementation,
+        modules/database.py:408-421; the reference's `standard` mode, which re-uploads both volumes every frame, is not
+        offered).  gt=False leaves origin / GT volumes as they are, like the reference."""
+        for s in (self.scenes if scenes is None else [scenes]):
+            self.scenes_est[s].volume = self._dev(self.scenes_est[s].volume, torch.float16)
+            self.fusion_weights[s] = self._dev(self.fusion_weights[s], torch.float16)
+            if gt:
+                self.origin[s] = torch.as_tensor(np.asarray(_np(self.origin[s]), dtype=np.float64))
+                self.scenes_gt[s].volume = self._dev(self.scenes_gt[s].volume, torch.float16)
+            if self.semantics:
+                self.ids_est[s].volume = self._dev(self.ids_est[s].volume, torch.uint8)
+                self.scores[s].volume = self._dev(self.scores[s].volume, torch.float16)
+                if gt and self.semantic_grid:
+                    self.ids_gt[s].volume = self._dev(self.ids_gt[s].volume, torch.uint8)
+
+    def _like(self, result, original):
+        """`result` (device tensor) in the form `original` was stored in."""
+        return _np(result) if isinstance(original, np.ndarray) else result
+
     def filter(self, value=2.):
         """modules/database.py:108-112."""
         for s in self.scenes:
-            low = self.fusion_weights[s] < value
-            self.scenes_est[s].volume[low] = self.initial_value
-            self.fusion_weights[s][low] = 0
+            est0, w0 = self.scenes_est[s].volume, self.fusion_weights[s]
+            est, w = self._dev(est0, torch.float16), self._dev(w0, torch.float16)
+            low = w < value
+            est[low] = self.initial_value
+            w[low] = 0
+            if est is not est0:                              # host-resident (after to_numpy()): store back in that form
+                self.scenes_est[s].volume = self._like(est, est0)
+            if w is not w0:
+                self.fusion_weights[s] = self._like(w, w0)
 
     def filter_semantics(self, value=5):
         """modules/database.py:114-116 (scipy median filter of the label volume), on the device."""
         for s in self.scenes:
-            self.ids_est[s].volume = metrics.median_filter_labels(self.ids_est[s].volume, size=value)
+            ids0 = self.ids_est[s].volume
+            self.ids_est[s].volume = self._like(metrics.median_filter_labels(self._dev(ids0, torch.uint8), size=value), ids0)
 
     def evaluate(self, mode='train', workspace=None):
         """modules/database.py:265-310: mse / mad / iou / acc (+ 'f1') averaged over the scenes, without leaving
@@ -115,7 +163,9 @@ class Database:
         for s in self.scenes:
             if not self.state[s]:
                 continue
-            r = metrics.evaluation(self.scenes_est[s].volume, self.scenes_gt[s].volume, self.fusion_weights[s] > 0)
+            r = metrics.evaluation(self._dev(self.scenes_est[s].volume, torch.float16),
+                                   self._dev(self.scenes_gt[s].volume, torch.float16),
+                                   self._dev(self.fusion_weights[s], torch.float16) > 0)
             per_scene[s] = r
             for k, v in r.items():
                 if workspace is not None:
@@ -131,8 +181,9 @@ class Database:
         for s in self.scenes:
             if not self.state[s]:
                 continue
-            r, cls_iou = metrics.semantic_evaluation(self.ids_est[s].volume, self.ids_gt[s].volume,
-                                                     self.fusion_weights[s] > 0, self.n_classes)
+            r, cls_iou = metrics.semantic_evaluation(self._dev(self.ids_est[s].volume, torch.uint8),
+                                                     self._dev(self.ids_gt[s].volume, torch.uint8),
+                                                     self._dev(self.fusion_weights[s], torch.float16) > 0, self.n_classes)
             per_scene[s] = cls_iou
             for k, v in r.items():
                 if workspace is not None:
@@ -141,3 +192,11 @@ class Database:
         for k in total:
             total[k] /= len(self.scenes_est)
         return total, per_scene
+
+    def save(self, path=None, save_mode=None, scene_id=None):
+        """modules/database.py:180-261 writes HDF5 / PLY files with h5py, skimage and trimesh -- out of scope here (I/O,
+        SURVEY.md section 2 row 6).  Kept as an explicit no-op for the reference's 'test' call sites with an unknown mode
+        (the reference itself does nothing for modes other than ply / tsdf / test); anything else raises."""
+        if save_mode in ('ply', 'tsdf', 'test'):
+            raise NotImplementedError("Database.save(%r): mesh / HDF5 export is out of scope of the B200 fusion path; "
+                                      "use the reference's writers on database.to_numpy() volumes" % (save_mode,))

@@ -275,7 +275,17 @@ class FusionNetEngine:
             self.plan.append(('conv', arr, 1, c.cin, c.cout, c.taps, c.act, c.slope, self.scale if last else 1.0))
             cur, cs = dst, ds
 
-    def forward(self, vals, wts, frame, sem_frame=None):
+    def pack_target(self, frame, sem_frame=None):
+        """What Extractor.forward(pack=...) needs to write this engine's input rows itself: (buf_a, buf_b, last_a, last_b, stride)."""
+        _lib.require_cuda(frame, sem_frame)
+        frame = frame.detach().float().contiguous()
+        if self.two:
+            assert sem_frame is not None
+            sem_frame = sem_frame.detach().float().contiguous()
+        return (self.in_bufs[0], self.in_bufs[1] if self.two else None, frame.reshape(-1), sem_frame.reshape(-1) if self.two else None,
+                self.Cd)
+
+    def forward(self, vals, wts, frame, sem_frame=None, packed=False):
         """vals / wts: (1,N,P) f32 pixel-major (Extractor output), frame: (1,h,w) f32 depth,
         sem_frame: (1,h,w) f32 normalised labels (1+id)/n_classes (modules/pipeline.py:96).
         Returns est (1,N,P) f32 (a buffer owned by the engine, overwritten by the next call)."""
@@ -290,9 +300,10 @@ class FusionNetEngine:
             sem_frame = sem_frame.detach().float().contiguous()
         with torch.cuda.device(dev), _lib.timed('fusionnet', dev):
             st = _lib.stream_ptr(dev)
-            _lib.check(L.ojdf_pack_fusion_input(vals.data_ptr(), wts.data_ptr(), frame.data_ptr(),
-                                                sem_frame.data_ptr() if self.two else None, N, P, self.in_bufs[0].data_ptr(),
-                                                self.in_bufs[1].data_ptr() if self.two else None, self.Cd, st))
+            if not packed:                                       # packed: the extractor's gather already wrote the input rows
+                _lib.check(L.ojdf_pack_fusion_input(vals.data_ptr(), wts.data_ptr(), frame.data_ptr(),
+                                                    sem_frame.data_ptr() if self.two else None, N, P, self.in_bufs[0].data_ptr(),
+                                                    self.in_bufs[1].data_ptr() if self.two else None, self.Cd, st))
             for step in self.plan:
                 kind = step[0]
                 if kind == 'conv':

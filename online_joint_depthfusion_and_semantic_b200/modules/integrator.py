@@ -20,7 +20,15 @@ from .. import _lib
 
 class FrameUpdate(dict):
     """Whole-frame update: ray (N,6) f64, filtered_depth (N) f32, est (N,P) f32, tail, clamp,
-    optional semantics (N) u8 + scores (N) f32 per pixel."""
+    optional semantics (N) u8 + scores (N) f32 per pixel, optional `plan` (Integrator.plan(): the geometry half of the
+    step was already issued, forward() only applies the network output)."""
+
+
+class IntegrationPlan:
+    """Handle of an issued ojdf_integrate_plan: the workspace now holds this frame's entries grouped by voxel."""
+
+    def __init__(self, N, P, tail, shape, workspace, event, stream):
+        self.N, self.P, self.tail, self.shape, self.workspace, self.event, self.stream = N, P, tail, shape, workspace, event, stream
 
 
 class Integrator(torch.nn.Module):
@@ -31,12 +39,46 @@ class Integrator(torch.nn.Module):
         self.device = config.SETTINGS.device
         self.implementation = config.SETTINGS.implementation
         self._workspace = None
+        self._side = None
+
+    def plan(self, ray, filtered_depth, P, tail, volume_shape, side_stream=True):
+        """Issue the geometry half of the integration (count / offsets / scatter: needs only the per-ray records and the
+        masked depth) -- on a side stream by default, so it overlaps whatever the caller enqueues next on the current
+        stream (the networks).  forward() with the returned plan in the FrameUpdate then runs only the apply kernels.
+        The side stream first waits for the current stream: the records are ready and the previous frame's apply (which
+        used the same workspace) is done."""
+        _lib.require_cuda(ray, filtered_depth)
+        dev = ray.device
+        N = ray.shape[0]
+        X, Y, Z = (int(v) for v in volume_shape)
+        filt = filtered_depth.detach().float().reshape(N).contiguous()
+        if N * int(tail) == 0:
+            return IntegrationPlan(N, int(P), int(tail), (X, Y, Z), None, None, None)
+        ws = self._get_workspace(N * int(tail) * 8, dev)
+        cur = torch.cuda.current_stream(dev)
+        st = cur
+        if side_stream:
+            if self._side is None or self._side.device != dev:
+                self._side = torch.cuda.Stream(device=dev)
+            st = self._side
+            st.wait_stream(cur)
+        with torch.cuda.device(dev), torch.cuda.stream(st), _lib.timed('integrate_plan', dev):
+            _lib.check(_lib.lib().ojdf_integrate_plan(_lib.ptr(ray), _lib.ptr(filt), N, int(P), int(tail), X, Y, Z, ws.data_ptr(),
+                                                      ws.numel(), st.cuda_stream))
+        ev = None
+        if side_stream:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            ray.record_stream(st)
+            filt.record_stream(st)
+        return IntegrationPlan(N, int(P), int(tail), (X, Y, Z), ws, ev, st)
 
     def _get_workspace(self, entries, dev):
         L = _lib.lib()
         need = int(L.ojdf_integrate_workspace_bytes(int(entries)))
         if need == 0:
-            raise _lib.OjdfError('ojdf: %d entries do not fit the 32-bit entry index' % entries)
+            raise _lib.OjdfError('ojdf: cannot size an integration workspace for %d entries (must be 1 .. 2^31 - 2049: '
+                                 'entries are indexed with 32 bits)' % entries)
         ws = self._workspace
         if ws is None or ws.numel() < need or ws.device != dev:
             ws = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -73,13 +115,25 @@ class Integrator(torch.nn.Module):
             if do_sem:
                 ids = updates['semantics'].detach().reshape(N).to(torch.uint8).contiguous()
                 sc = updates['scores'].detach().reshape(N).float().contiguous()
-            ws = self._get_workspace(N * tail * 8, dev)
-            with torch.cuda.device(dev), _lib.timed('integrate', dev):
-                _lib.check(L.ojdf_integrate(
-                    _lib.ptr(ray), _lib.ptr(filt), _lib.ptr(est), N, P, tail, float(updates['clamp']),
-                    values_volume.data_ptr(), weights_volume.data_ptr(), X, Y, Z, _lib.ptr(ids), _lib.ptr(sc),
-                    semantics_volume.data_ptr() if do_sem else None, scores_volume.data_ptr() if do_sem else None,
-                    int(do_sem), ws.data_ptr(), ws.numel(), stream))
+            if N * tail == 0:                                       # empty frame: nothing to integrate
+                return values_volume, weights_volume, semantics_volume, scores_volume
+            plan = updates.get('plan')
+            args = (N, P, tail, float(updates['clamp']), values_volume.data_ptr(), weights_volume.data_ptr(), X, Y, Z,
+                    _lib.ptr(ids), _lib.ptr(sc), semantics_volume.data_ptr() if do_sem else None,
+                    scores_volume.data_ptr() if do_sem else None, int(do_sem))
+            if plan is not None:
+                if (plan.N, plan.P, plan.tail, plan.shape) != (N, P, tail, (X, Y, Z)) or plan.workspace is None:
+                    raise ValueError('integration plan was made for another frame / volume shape')
+                ws = plan.workspace
+                if plan.event is not None:
+                    torch.cuda.current_stream(dev).wait_event(plan.event)
+                with torch.cuda.device(dev), _lib.timed('integrate', dev):
+                    _lib.check(L.ojdf_integrate_apply(_lib.ptr(est), *args, ws.data_ptr(), ws.numel(), stream))
+            else:
+                ws = self._get_workspace(N * tail * 8, dev)
+                with torch.cuda.device(dev), _lib.timed('integrate', dev):
+                    _lib.check(L.ojdf_integrate(_lib.ptr(ray), _lib.ptr(filt), _lib.ptr(est), *args, ws.data_ptr(), ws.numel(),
+                                                stream))
         else:
             values = updates['values'].to(dev).detach().float().contiguous()
             M1 = values.numel()

@@ -19,6 +19,8 @@ FusionNet_v1 is not provided: it cannot be constructed in the reference either
 import torch
 from torch import nn
 
+from ._engine_cache import EngineOwner
+
 _VORTEX_RATES = (1, 3, 9, 27)
 
 
@@ -102,38 +104,49 @@ class VortexPooling(nn.Module):
         return self.final(torch.cat(feats, dim=1))
 
 
-class _EngineMixin:
+class _EngineMixin(EngineOwner):
     """Eval-mode, no-grad, CUDA forwards run on libojdf's fused kernels (fusion_engine.py); anything
     that needs autograd (training, row a2) runs the module's torch forward.  The launch plan is
-    dropped whenever parameters can have changed (train(), load_state_dict(), .to()/.cuda())."""
+    dropped whenever parameters can have changed: train(), .to()/.cuda(), load_state_dict() on this module
+    or on a parent, in-place writes (see _engine_cache.py)."""
     _engine = None
     use_engine = True
 
-    def train(self, mode=True):
+    def _drop_engines(self):
         self._engine = None
+
+    def train(self, mode=True):
+        self._invalidate()
         return super().train(mode)
 
     def _apply(self, fn, *a, **k):
-        self._engine = None
+        self._invalidate()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._engine = None
+        self._invalidate()
         return super().load_state_dict(*a, **k)
 
     def engine_ready(self, ref_tensor):
         return (self.use_engine and not self.training and not torch.is_grad_enabled() and ref_tensor.is_cuda
                 and not (hasattr(self, 'block') and self.config.use_semantics))
 
-    def forward_pixel_major(self, vals, wts, frame, sem_frame=None):
-        """vals/wts (1,N,P) pixel-major, frame (1,h,w) depth, sem_frame (1,h,w) normalised labels
-        -> est (1,N,P), already multiplied by output_scale."""
+    def engine_for(self, h, w, device):
+        """The launch plan for (h, w) frames on `device` (built on first use, rebuilt when parameters changed)."""
         from .fusion_engine import FusionNetEngine
-        h, w = frame.shape[-2:]
+        self._hook_load_state_dict()
+        self.engines_current()
         e = self._engine
-        if e is None or (e.h, e.w) != (h, w) or e.device != vals.device:
-            e = self._engine = FusionNetEngine(self, h, w, vals.device)
-        return e.forward(vals, wts, frame, sem_frame)
+        if e is None or (e.h, e.w) != (int(h), int(w)) or e.device != torch.device(device):
+            e = self._engine = FusionNetEngine(self, h, w, device)
+        return e
+
+    def forward_pixel_major(self, vals, wts, frame, sem_frame=None, packed=False):
+        """vals/wts (1,N,P) pixel-major, frame (1,h,w) depth, sem_frame (1,h,w) normalised labels
+        -> est (1,N,P), already multiplied by output_scale.  packed=True: the input rows were already written into the
+        engine's buffers (Extractor.forward(pack=engine.pack_target(...)))."""
+        h, w = frame.shape[-2:]
+        return self.engine_for(h, w, vals.device).forward(vals, wts, frame, sem_frame, packed=packed)
 
     def _forward_engine_nchw(self, x):
         """Same call surface as the reference forward (dict of NCHW tensors in, NCHW tensor out)."""

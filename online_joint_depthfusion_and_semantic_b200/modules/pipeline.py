@@ -48,7 +48,9 @@ class Pipeline(nn.Module):
         self._extractor = Extractor(config)
         self._integrator = Integrator(config)
         self.use_cuda_graphs = True          # replay the fixed-shape networks as CUDA graphs in inference
+        self.plan_ahead = True               # issue the geometry half of the integration on a side stream, early
         self._seg_graph = None
+        self._seg_graph_token = (None, None)
 
     def train(self, mode=True):
         self._seg_graph = None               # captured graphs hold parameter addresses / modes
@@ -78,13 +80,24 @@ class Pipeline(nn.Module):
         key = self.config.DATA.input
         image = data['image'].to(self.device)
         aux = None if key == 'image' else data[key].to(self.device)
-        graphable = (self.use_cuda_graphs and image.is_cuda and not torch.is_grad_enabled()
-                     and not self._semantic_2d_network.training)
+        net = self._semantic_2d_network
+        graphable = (self.use_cuda_graphs and image.is_cuda and not torch.is_grad_enabled() and not net.training)
         if not graphable:
             return self._segmentation_eager(image, aux)
-        if self._seg_graph is None:
+        # The captured graph replays kernels that point into the AdapNet++ launch plan: it is only valid while that very
+        # plan object is alive and its parameters are unchanged (eval() / .to() / load_state_dict() / in-place writes on
+        # the network drop the plan, modules/_engine_cache.py).
+        net._hook_load_state_dict()
+        net.engines_current()
+        if self._seg_graph is not None and any(a is not b for a, b in zip(net.engine_token(), self._seg_graph_token)):
+            self._seg_graph = None
+        fresh = self._seg_graph is None
+        if fresh:
             self._seg_graph = GraphedCall(lambda *a: self._segmentation_eager(a[0], a[1] if len(a) > 1 else None))
-        return self._seg_graph(image) if aux is None else self._seg_graph(image, aux)
+        out = self._seg_graph(image) if aux is None else self._seg_graph(image, aux)
+        if fresh:
+            self._seg_graph_token = net.engine_token()
+        return out
 
     def _semantic_frame(self, batch, as_uint8):
         """(scores f32, ids) per pixel, or (None, None): modules/pipeline.py:181-193,277-292."""
@@ -95,7 +108,7 @@ class Pipeline(nn.Module):
             with torch.no_grad(), _lib.timed('adapnet', self.device):
                 scores, ids = self._segmentation(batch).max(dim=-1)
         elif strategy == 'gt':
-            ids = batch['semantic_gt'].long()
+            ids = batch['semantic_gt'].to(self.device).long()
             scores = torch.ones_like(ids).float()
         else:
             raise ValueError('Error! Valid value for DATA.semantic_strategy are "gt" or "predict".')
@@ -115,16 +128,29 @@ class Pipeline(nn.Module):
             inputs['semantic_frame'] = (1 + semantics.unsqueeze(-1).float()) / self.n_classes      # (0, 1]
         return {k: v.permute(0, 3, 1, 2).contiguous() for k, v in inputs.items()}
 
-    def _fusion(self, inputs, values):
+    def _fusion(self, inputs, values, packed=False):
         b, _, h, w = self._shape
         net = self._fusion_network
         if getattr(net, 'engine_ready', None) is not None and net.engine_ready(values['fusion_values']):
             # pixel-major in, pixel-major out: the extractor's layout is the kernels' layout
             sem = inputs['semantic_frame'].reshape(b, h, w) if 'semantic_frame' in inputs else None
             return net.forward_pixel_major(values['fusion_values'], values['fusion_weights'],
-                                           inputs['tsdf_frame'].reshape(b, h, w), sem)[..., :self.n_points]
+                                           inputs['tsdf_frame'].reshape(b, h, w), sem, packed=packed)[..., :self.n_points]
         est = net(inputs).permute(0, 2, 3, 1)[..., :self.n_points]
         return est.reshape(b, h * w, self.n_points)
+
+    def _pack_target(self, frame, sem_ids):
+        """FusionNet's own input buffers, if its launch plan will run this frame: the extractor's gather then writes the
+        [values | weights | depth or label] rows itself (modules/pipeline.py:74-102 without the packing pass)."""
+        net = self._fusion_network
+        if getattr(net, 'engine_ready', None) is None or not net.engine_ready(frame):
+            return None
+        b, _, h, w = self._shape
+        sem = None
+        if self.config.FUSION_MODEL.use_semantics:
+            assert sem_ids is not None
+            sem = (1 + sem_ids.reshape(b, h, w).float()) / self.n_classes
+        return net.engine_for(h, w, frame.device).pack_target(frame.reshape(b, h, w), sem)
 
     # ---- a12: loss tensors (modules/pipeline.py:104-135) ------------------------------------------
     def _prepare_fusion_output(self, values, tsdf_est, filtered_frame=None, values_gt=None):
@@ -160,17 +186,28 @@ class Pipeline(nn.Module):
     def fuse(self, batch, database, device):
         self.device = device
         self._shape = batch['image'].shape
-        scores, sem_ids = self._semantic_frame(batch, as_uint8=False)
         frame, filtered_frame = self._frames(batch)
         scene_id = batch['frame_id'][0].split('/')[0]
         volume = database[scene_id]
+        # per-ray records first: they only need depth and pose, and with them the geometry half of the integration
+        # (grouping the frame's (ray, sample, corner) entries by voxel) is issued on a side stream, where it overlaps the
+        # two networks; only the light apply kernels remain after FusionNet
+        rays = plan = None
+        if frame.is_cuda and self.plan_ahead:
+            rays = self._extractor.rays(frame, batch['extrinsics'], batch['intrinsics'], volume['origin'], volume['resolution'])
+            plan = self._integrator.plan(rays['ray'], filtered_frame, self.n_points, self.config.FUSION_MODEL.n_tail_points,
+                                         volume['current'].shape)
+        scores, sem_ids = self._semantic_frame(batch, as_uint8=False)
+        pack = self._pack_target(frame, sem_ids) if frame.is_cuda else None
         values = self._extractor.forward(frame, batch['extrinsics'], batch['intrinsics'], volume['current'],
-                                         volume['weights'], volume['origin'], volume['resolution'])
-        tsdf_est = self._fusion(self._prepare_fusion_input(frame, values, sem_ids), values)
+                                         volume['weights'], volume['origin'], volume['resolution'], rays=rays, pack=pack)
+        tsdf_est = self._fusion(self._prepare_fusion_input(frame, values, sem_ids), values, packed=pack is not None)
         sem = self.config.DATA.semantics
         if sem:
             sem_ids = sem_ids.type(torch.uint8)
         updates = self._prepare_volume_update(values, tsdf_est, filtered_frame, sem_ids if sem else None, scores)
+        if plan is not None:
+            updates['plan'] = plan
         tsdf, weights, ids, sc = self._integrator.forward(updates, volume['current'], volume['weights'],
                                                           volume['scores'] if sem else None,
                                                           volume['ids_est'] if sem else None)

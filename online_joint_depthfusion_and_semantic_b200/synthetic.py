@@ -177,3 +177,30 @@ class SyntheticScene:
             'semantic_gt': lab.unsqueeze(0),
             'frame_id': ['%s/0/%d' % (self.name, i)],
         }
+
+
+def seeded_parameters(module, seed, scale=1.0):
+    """Fill every parameter and buffer of `module` from a seeded generator, in sorted state_dict key order, so that two
+    modules with the same key set (the reference's network and this package's mirror) get bit-identical values no
+    matter in which order their constructors created the tensors.  Weights ~ N(0, fan-in scaled), BatchNorm statistics
+    non-trivial (running_var in [0.5, 1.5]), like a trained checkpoint has.  No checkpoint exists offline."""
+    gen = torch.Generator().manual_seed(int(seed))
+    sd = module.state_dict()
+    with torch.no_grad():
+        for k in sorted(sd):
+            t = sd[k]
+            if not t.is_floating_point():
+                continue                                   # num_batches_tracked
+            if k.endswith('running_var'):
+                v = 0.5 + torch.rand(t.shape, generator=gen)
+            elif k.endswith('running_mean'):
+                v = 0.1 * torch.randn(t.shape, generator=gen)
+            elif t.dim() >= 2:
+                fan_in = t[0].numel()
+                v = torch.randn(t.shape, generator=gen) * (scale * (2.0 / fan_in) ** 0.5)
+            elif k.endswith('weight'):
+                v = 0.8 + 0.4 * torch.rand(t.shape, generator=gen)     # BatchNorm gamma
+            else:
+                v = 0.05 * torch.randn(t.shape, generator=gen)         # biases / BatchNorm beta
+            t.copy_(v.to(t.dtype))
+    return module

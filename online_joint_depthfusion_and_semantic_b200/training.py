@@ -70,18 +70,35 @@ class ShardedFusionTrainer:
         self.iteration = 0
 
     def _flat_bucket(self):
-        """All FusionNet gradients as views into one contiguous buffer -> a single collective."""
+        """All FusionNet gradients as views into one contiguous buffer -> a single collective.
+
+        The views are re-checked on every call: `optimizer.zero_grad()` / `model.zero_grad()` default to
+        set_to_none=True (the reference calls them around evaluation, train_fusion.py:176,194), after which autograd
+        allocates fresh, unrelated .grad tensors -- all-reducing the stale bucket would then silently desynchronise the
+        replicas.  A parameter whose .grad is not the expected view is re-attached (its gradient, if any, is copied in)."""
         if self._bucket is None:
             n = sum(p.numel() for p in self.params)
             self._bucket = torch.zeros(n, dtype=self.params[0].dtype, device=self.params[0].device)
-            off = 0
+            self._offsets, off = [], 0
             for p in self.params:
-                view = self._bucket[off:off + p.numel()].view_as(p)
-                if p.grad is not None:
-                    view.copy_(p.grad)
-                p.grad = view
+                self._offsets.append(off)
                 off += p.numel()
+        base, esz = self._bucket.data_ptr(), self._bucket.element_size()
+        for p, off in zip(self.params, self._offsets):
+            g = p.grad
+            if g is not None and g.data_ptr() == base + off * esz and g.is_contiguous() and g.numel() == p.numel():
+                continue
+            view = self._bucket[off:off + p.numel()].view_as(p)
+            if g is not None:
+                view.copy_(g)
+            else:
+                view.zero_()
+            p.grad = view
         return self._bucket
+
+    def zero_grad(self):
+        """Use this instead of optimizer.zero_grad(): zeroes the bucket and keeps the gradient views attached."""
+        self._flat_bucket().zero_()
 
     def broadcast_parameters(self, src=0):
         if self.world > 1:
@@ -100,6 +117,7 @@ class ShardedFusionTrainer:
         self.iteration += 1
         stepped = False
         if self.iteration % self.accumulation_steps == 0 or last:
+            bucket = self._flat_bucket()                         # re-attach anything that replaced a gradient view
             if self.world > 1:
                 dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group)
                 bucket.div_(self.world)

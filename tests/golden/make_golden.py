@@ -170,6 +170,47 @@ def case_integrate(name, h, w, G, seed, ext, do_sem=True, test=True):
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **d)
 
 
+def case_integrate_nan(name, G=16, seed=31):
+    """0/0 -> NaN (modules/integrator.py:82): the reference Integrator.forward on a hand-made `updates` dict in which
+    some voxels with a zero prior weight only ever receive zero-weight entries (in real frames: corner weights that
+    underflow in the f64 -> f32 cast, SURVEY.md section 7 "0/0 NaN").  Also has voxels hit by several entries of which
+    only some are zero, entries outside the grid, and a voxel whose prior weight is non-zero but whose entries are all
+    zero (stays finite)."""
+    _, ref_integrator, *_ = ref_env()
+    rs = np.random.RandomState(seed)
+    Nv, T = 40, 7
+    idx = rs.randint(-2, G + 2, (1, Nv, T, 8, 3)).astype(np.int64)
+    wts = rs.uniform(0.0, 1.0, (1, Nv, T, 8))
+    wts[rs.rand(1, Nv, T, 8) < 0.35] = 0.0
+    vals = rs.uniform(-0.1, 0.1, (1, Nv, T)).astype(np.float32)
+    tsdf, wv = rand_volumes(rs, G, zero_weight_frac=0.6)
+    # make sure the interesting cases exist: a fresh voxel with only zero-weight entries, and one with prior weight
+    wv[3, 4, 5], wv[6, 7, 8] = 0.0, 2.5
+    for vx in ((3, 4, 5), (6, 7, 8)):                          # nobody else touches the two special voxels
+        hit = (idx == np.array(vx)).all(-1)
+        idx[hit] = -1
+    for n, vx in enumerate(((3, 4, 5), (6, 7, 8))):
+        idx[0, n, :3, :2] = vx
+        wts[0, n, :3, :2] = 0.0
+    ids_vol = rs.randint(0, 6, (G, G, G)).astype(np.uint8)
+    sc_vol = (rs.randint(0, 5, (G, G, G)) / 4.0).astype(np.float16)
+    pix_ids = rs.randint(0, 6, (1, Nv, T, 1)).astype(np.uint8)
+    pix_sc = (rs.randint(0, 5, (1, Nv, T, 1)) / 4.0).astype(np.float32)
+    cfg = make_config(8, 8, semantics=True)
+    upd = dict(values=torch.from_numpy(vals), indices=torch.from_numpy(idx), weights=torch.from_numpy(wts),
+               points=torch.zeros(1, Nv, T, 3, dtype=torch.float64), semantics=torch.from_numpy(pix_ids),
+               scores=torch.from_numpy(pix_sc))
+    t0, w0, i0, s0 = (torch.from_numpy(a.copy()) for a in (tsdf, wv, ids_vol, sc_vol))
+    v1, w1, i1, s1 = ref_integrator.Integrator(cfg).forward(upd, t0, w0, s0, i0, test=True)
+    nan = int(np.isnan(v1.numpy().astype(np.float32)).sum())
+    assert nan > 0 and np.isnan(np.float32(v1[3, 4, 5])) and np.isfinite(np.float32(v1[6, 7, 8]))
+    print('%-22s entries=%d NaN voxels=%d' % (name, Nv * T * 8, nan))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), values=vals, indices=idx.astype(np.int16), weights=wts,
+                        semantics=pix_ids, scores=pix_sc, G=np.int32(G),
+                        tsdf0=h16(tsdf), wvol0=h16(wv), ids0=ids_vol, scores0=h16(sc_vol),
+                        tsdf1=h16(v1.numpy()), wvol1=h16(w1.numpy()), ids1=i1.numpy(), scores1=h16(s1.numpy()))
+
+
 class ClassicUpdate(torch.nn.Module):
     """Stand-in for FusionNet inside the REFERENCE Pipeline: the classical TSDF update
     est[n,k] = (4-k)*resolution, so that the multi-frame
@@ -247,6 +288,47 @@ def case_pipeline(name, h, w, G, n_frames, frame_ids):
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **d)
 
 
+def case_training(name, h, w, G, n_frames, frame_ids):
+    """Reference Pipeline.fuse_training (modules/pipeline.py:251-363) over a few frames: the loss tensors
+    tsdf_est / tsdf_fused / tsdf_target of every frame (incl. the reference's _prepare_fusion_output + masking,
+    :104-135,365-405, and the second extraction from the GT volume) and the volumes after the `test=False` integration.
+    FusionNet is replaced by the classical update so no convolution is involved; gt semantics."""
+    *_, ref_pipeline, _, _ = ref_env()
+    from online_joint_depthfusion_and_semantic_b200.synthetic import SyntheticScene
+    scene = SyntheticScene(name='synth0', grid=G, h=h, w=w, n_frames=n_frames, seed=5)
+    cfg = make_config(h, w, semantics=True, strategy='gt')
+    pipe = ref_pipeline.Pipeline(cfg)
+    pipe._fusion_network = ClassicUpdate(scene.resolution)
+    pipe.train()
+    db = FakeDatabase('synth0', G, scene.origin, scene.resolution)
+    gt, _ = scene.gt_volumes()
+    db.scenes_gt['synth0'].volume = gt
+    d = dict(n_frames=np.int32(len(frame_ids)), G=np.int32(G), origin=scene.origin, res=np.float64(scene.resolution),
+             gt=h16(gt.numpy()))
+    pcls = []
+    ref_forward = pipe._extractor.forward
+
+    def recording_forward(*a, **k):
+        out = ref_forward(*a, **k)
+        pcls.append(out['pcl'].numpy().copy())
+        return out
+    pipe._extractor.forward = recording_forward
+    for j, i in enumerate(frame_ids):
+        b = scene.frame(i)
+        for k in ('tof_depth', 'mask', 'extrinsics', 'intrinsics', 'semantic_gt'):
+            d['f%d_%s' % (j, k)] = b[k].numpy().copy()
+        b['image'] = torch.zeros(1, 3, h, w)
+        out = pipe.fuse_training(b, db, torch.device('cpu'))
+        d['f%d_pcl' % j] = pcls[-1]
+        for k in ('tsdf_est', 'tsdf_fused', 'tsdf_target'):
+            d['f%d_%s' % (j, k)] = out[k].detach().numpy().copy()
+    d.update(tsdf=h16(db.scenes_est['synth0'].volume.numpy()), wvol=h16(db.fusion_weights['synth0'].numpy()),
+             ids=db.ids_est['synth0'].volume.numpy(), scores=h16(db.scores['synth0'].volume.numpy()))
+    assert int((d['ids'] != 0).sum()) == 0                                   # test=False: the semantic volumes stay untouched
+    print('%-22s frames=%d Nv(last)=%d' % (name, len(frame_ids), out['tsdf_fused'].shape[1]))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **d)
+
+
 def main():
     torch.set_num_threads(1)
     torch.manual_seed(1911)
@@ -259,7 +341,9 @@ def main():
     case_integrate('integrate_24x32_g32_sem', 24, 32, 32, seed=21, ext=2.4, do_sem=True, test=True)
     case_integrate('integrate_24x32_g32_train', 24, 32, 32, seed=22, ext=2.4, do_sem=True, test=False)
     case_integrate('integrate_48x64_g24_dup', 48, 64, 24, seed=23, ext=3.0, do_sem=True, test=True)
+    case_integrate_nan('integrate_updates_nan_g16')
     case_pipeline('pipeline_48x64_g48', 48, 64, 48, n_frames=12, frame_ids=[0, 1, 2, 5])
+    case_training('training_24x32_g32', 24, 32, 32, n_frames=12, frame_ids=[0, 1, 4])
 
 
 if __name__ == '__main__':

@@ -46,6 +46,26 @@ def main():
     stride = 97
     out['v3_sem_forward'] = dict(seed=seed, h=h, w=w, sample_stride=stride,
                                  sample_values=[float(v) for v in y.reshape(-1)[::stride]])
+    # AdapNet++ stage 2 (modules/adapnet.py:356-415): the reference's CPU logits for seeded parameters (filled in sorted
+    # state_dict key order: identical values in the reference module and in the mirror) and a seeded input, with the
+    # eval-time-active bottleneck dropout switched off (modules/adapnet.py:80-82)
+    from online_joint_depthfusion_and_semantic_b200.synthetic import seeded_parameters
+    cfg.SEMANTIC_2D_MODEL.stage = 2
+    seg = seeded_parameters(ref_adapnet.AdapNet(cfg.SEMANTIC_2D_MODEL), 4321).eval()
+    for m in seg.modules():
+        if isinstance(m, ref_adapnet.BottleneckSSMA):
+            m.dropout = False
+    ah, aw = 32, 48
+    gen = torch.Generator().manual_seed(99)
+    m1, m2 = torch.randn(1, 3, ah, aw, generator=gen), torch.randn(1, 3, ah, aw, generator=gen)
+    with torch.no_grad():
+        res, aux1, aux2 = seg(m1, m2)
+    astride = 53
+    out['adapnet_stage2_forward'] = dict(param_seed=4321, input_seed=99, h=ah, w=aw, sample_stride=astride,
+                                         logits_shape=list(res.shape), logits_abs_max=float(res.abs().max()),
+                                         sample_values=[float(v) for v in res.reshape(-1)[::astride]],
+                                         aux1_sample=[float(v) for v in aux1.reshape(-1)[::astride * 7]],
+                                         aux2_sample=[float(v) for v in aux2.reshape(-1)[::astride * 7]])
     json.dump(out, open(os.path.join(HERE, 'nets.json'), 'w'), indent=1)
     print({k: (v if 'sample_values' not in v else '...') for k, v in out.items()})
 

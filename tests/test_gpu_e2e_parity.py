@@ -1,0 +1,72 @@
+"""End-to-end parity of BASELINE.json's metric ("F-score & mIoU parity"), SURVEY.md App. E "multi-frame drift":
+
+  * 100 frames of the headline configuration (240x320 RGB-D -> 256^3, AdapNet++ stage 2 + FusionNet_v3(sem)) fused by
+    the CUDA pipeline and by the CPU port (oracle C + the same torch modules on the CPU), then filter / filter_semantics(5)
+    / evaluate / evaluate_semantics exactly as test_fusion.py:82-108: |delta| <= 0.5 pt on iou / acc / F1 / mIoU;
+  * the UNMODIFIED reference driver (test_fusion.py) with INTEGRATION.md option A's module swap on the GPU against
+    the same driver with the reference's own modules on the CPU (one thread: the reference's semantic scatter is only
+    deterministic single-threaded), metrics from the reference's own Database + utils/metrics.py.
+"""
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
+
+pytestmark = pytest.mark.gpu
+TOL_POINTS = 0.5
+
+
+def _check(out, name):
+    dst = os.path.join(ROOT, 'gpurun_out')
+    if os.path.isdir(dst):
+        with open(os.path.join(dst, name), 'w') as f:
+            json.dump(out, f, indent=1)
+    for k in ('iou', 'acc', 'f1', 'Mean IoU', 'Mean Acc'):
+        assert 100.0 * out['abs_diff'][k] <= TOL_POINTS, (k, out['cuda'][k], out['cpu_port'][k])
+    for k in ('mse', 'mad'):                                    # clipped-TSDF errors: relative agreement
+        assert out['abs_diff'][k] <= 1e-3 * max(out['cpu_port'][k], 1e-9), (k, out['cuda'][k], out['cpu_port'][k])
+    # drift of the volumes themselves: the 1e-6 differences of the network outputs move fp16 running means by an ulp
+    # now and then (bounded: the TSDF is clamped to +-0.1 every frame), never by more than a few 1e-3 of the range
+    v = out['volumes']
+    assert v['tsdf_mean_abs_diff'] <= 2e-4 and v['tsdf_max_abs_diff'] <= 0.2, v
+
+
+@pytest.mark.timeout(1500)
+def test_parity_100_frames_headline_configuration():
+    import parity_report
+    out = parity_report.parity(frames=100, h=240, w=320, grid=256)
+    _check(out, 'parity_100f_240x320_g256.json')
+
+
+@pytest.mark.timeout(900)
+def test_parity_gt_semantics_40_frames():
+    """Same protocol with `semantic_strategy: gt` (no AdapNet++: labels are exact on both sides, so mIoU is a non-trivial
+    number and any label-volume difference comes from the integrator alone -- there must be none)."""
+    import parity_report
+    out = parity_report.parity(frames=40, h=240, w=320, grid=256, strategy='gt')
+    _check(out, 'parity_40f_gt_240x320_g256.json')
+    assert out['cuda']['Mean IoU'] > 0.05
+    assert out['volumes']['label_voxels_differing'] == 0
+
+
+@pytest.mark.timeout(900)
+def test_unmodified_test_fusion_driver_with_option_a_swap_matches_the_reference():
+    from baseline import harness
+    from test_drive_reference_cpu import run_harness
+    if harness.ref_root() is None:
+        pytest.skip('reference tree not available (python baseline/install_ref.py in the build container)')
+    shape = ['--frames', '24', '--h', '48', '--w', '64', '--grid', '48']
+    ours = run_harness('drive', '--impl', 'ours', '--gpu', '1', *shape)
+    ref = run_harness('drive', '--impl', 'reference', '--gpu', '0', '--threads', '1', *shape)
+    assert ours['reached'] == 'end' and ref['reached'] == 'end'
+    for k in ('iou', 'acc'):
+        assert abs(ours['eval'][k] - ref['eval'][k]) * 100.0 <= TOL_POINTS, (k, ours['eval'], ref['eval'])
+    for k in ('mse', 'mad'):
+        assert abs(ours['eval'][k] - ref['eval'][k]) <= 1e-3 * ref['eval'][k], (k, ours['eval'], ref['eval'])
+    for k in ('Mean IoU', 'Mean Acc'):
+        assert abs(ours['semantic_eval'][k] - ref['semantic_eval'][k]) * 100.0 <= TOL_POINTS, (k, ours['semantic_eval'], ref['semantic_eval'])

@@ -197,6 +197,10 @@ def _random_frame(rs, h, w, G, ext, lo, hi, hole=0.05):
 
 @pytest.mark.parametrize('h,w,G,ext,lo,hi', [
     (240, 320, 128, 3.2, 0.3, 2.5),       # benchmark frame size, oracle-sized grid
+    (240, 320, 256, 3.2, 0.3, 2.5),       # BASELINE.json configs[1]: the headline frame and grid, bit for bit
+    (240, 320, 48, 3.2, 0.051, 0.08),     # near-camera surface at the full frame size: thousands of blocks (several
+                                          # waves) and dozens of over-long voxels -> the cooperative finalize path
+                                          # races with the regular blocks unless idle slots are skipped
     (60, 80, 64, 3.2, 0.051, 0.08),       # surface 5-8 cm from the eye: hundreds of entries per voxel (warp path)
     (120, 160, 32, 3.2, 0.051, 0.12),     # ... >10^4 entries per voxel (block path), 100 mm voxels
     (7, 5, 16, 1.0, 0.2, 0.6),            # ragged tiny frame, mostly out of grid
@@ -241,6 +245,59 @@ def test_extract_and_integrate_vs_oracle_seeded(h, w, G, ext, lo, hi):
     assert np.array_equal(a[~nan_a], b[~nan_b])
     assert np.array_equal(ids_d.cpu().numpy(), i_o)
     assert np.array_equal(_bits(sc_d), s_o)
+
+
+def test_integrate_zero_over_zero_nan_vs_reference_golden(golden):
+    """The reference's `updates` form with zero-weight entries on zero-weight voxels: NaN stored exactly where the
+    reference stores it (modules/integrator.py:82), everything else bit-exact."""
+    g = golden('integrate_updates_nan_g16')
+    cfg = fusion_config(8, 8)
+    integ = Integrator(cfg)
+    tsdf, wvol = _f16(g['tsdf0']), _f16(g['wvol0'])
+    ids, sc = torch.from_numpy(g['ids0'].copy()).to(DEV), _f16(g['scores0'])
+    upd = dict(values=torch.from_numpy(g['values']).to(DEV), indices=torch.from_numpy(g['indices'].astype(np.int64)).to(DEV),
+               weights=torch.from_numpy(g['weights']).to(DEV), semantics=torch.from_numpy(g['semantics']).to(DEV),
+               scores=torch.from_numpy(g['scores']).to(DEV))
+    integ.forward(upd, tsdf, wvol, sc, ids, test=True)
+    torch.cuda.synchronize()
+    got, want = _bits(tsdf), g['tsdf1']
+    nan_g, nan_w = np.isnan(got.view(np.float16)), np.isnan(want.view(np.float16))
+    assert int(nan_w.sum()) == 154 and np.array_equal(nan_g, nan_w)
+    assert np.array_equal(got[~nan_g], want[~nan_w]) and np.array_equal(_bits(wvol), g['wvol1'])
+    assert np.array_equal(ids.cpu().numpy(), g['ids1']) and np.array_equal(_bits(sc), g['scores1'])
+
+
+def test_non_finite_depth_pixels_are_dropped_like_the_reference():
+    """NaN / Inf depth pixels: the reference's double -> int64 conversion yields INT64_MIN, the corner fails
+    get_index_mask (modules/extractor.py:596-607) and the entry is dropped; nothing may land in voxel (0,0,0)."""
+    rs = np.random.RandomState(5)
+    h, w, G = 24, 32, 32
+    depth, E, K, tsdf, wv, origin, res = _random_frame(rs, h, w, G, 2.4, 0.3, 1.5)
+    depth[0, 3, 4], depth[0, 10, 11], depth[0, 20, 7] = np.nan, np.inf, -np.inf
+    wv[0, 0, 0] = 0
+    cfg = fusion_config(h, w)
+    ex, integ = Extractor(cfg), Integrator(cfg)
+    t_d, w_d = torch.from_numpy(tsdf).to(DEV), torch.from_numpy(wv).to(DEV)
+    vals = ex.forward(torch.from_numpy(depth).to(DEV), torch.from_numpy(E[None]), torch.from_numpy(K[None]), t_d, w_d,
+                      torch.from_numpy(origin), res)
+    world = vals['pcl'][0].cpu().numpy()
+    N = h * w
+    est = rs.uniform(-0.15, 0.15, (N, 9)).astype(np.float32)
+    filt = depth.reshape(N).copy()
+    upd = FrameUpdate(ray=vals['ray'], filtered_depth=torch.from_numpy(filt).to(DEV), est=torch.from_numpy(est).to(DEV),
+                      tail=7, clamp=0.1)
+    cfg.DATA.semantics = ''
+    integ.forward(upd, t_d, w_d, None, None)
+    torch.cuda.synchronize()
+    t_o, w_o = tsdf.view(np.uint16).copy(), wv.view(np.uint16).copy()
+    oracle.integrate_frame(world, filt, est, E[:3, 3], origin, res, t_o, w_o)
+    assert np.array_equal(_bits(w_d), w_o)
+    a = _bits(t_d)
+    nan_a, nan_b = np.isnan(a.view(np.float16)), np.isnan(t_o.view(np.float16))
+    assert np.array_equal(nan_a, nan_b) and np.array_equal(a[~nan_a], t_o[~nan_b])
+    assert _bits(w_d)[0, 0, 0] == 0                                         # the NaN pixel did not poison voxel (0,0,0)
+    idx = vals['indices'][0].reshape(h, w, 9, 8, 3)
+    assert int(idx[3, 4].max()) < 0 and int(idx[10, 11].max()) < 0         # INT64_MIN like the CPU conversion
 
 
 def test_empty_and_fully_masked_frames():

@@ -46,8 +46,8 @@ def test_fuse_volumes_bit_exact_given_network_output(strategy, use_sem):
     captured = {}
     inner = pipe._fusion
 
-    def tap(inputs, values):
-        est = inner(inputs, values)
+    def tap(inputs, values, **kw):
+        est = inner(inputs, values, **kw)
         captured['est'] = est.detach()[0].cpu().numpy().copy()
         captured['world'] = values['pcl'][0].cpu().numpy().copy()
         captured['vals'] = values['fusion_values'][0].cpu().numpy().copy()
@@ -116,3 +116,61 @@ def test_no_semantics_config():
         pipe.fuse(scene.frame(0, device=DEV), db, DEV)
     torch.cuda.synchronize()
     assert int((db.fusion_weights['s0'] > 0).sum()) > 500
+
+
+class _ClassicUpdate(torch.nn.Module):
+    """The stand-in tests/golden/make_golden.py puts in place of FusionNet: est[n,k] = (4-k)*resolution."""
+
+    def __init__(self, res, n_points=9):
+        super().__init__()
+        self.res, self.n_points = res, n_points
+
+    def forward(self, x):
+        b, _, h, w = x['tsdf_values'].shape
+        k = torch.arange(self.n_points, dtype=torch.float32, device=x['tsdf_values'].device)
+        return (((self.n_points // 2) - k) * self.res).view(1, -1, 1, 1).expand(b, -1, h, w).contiguous()
+
+
+def test_fuse_training_values_vs_reference_golden(golden):
+    """Row a2 / a12: `Pipeline.fuse_training` against the REFERENCE's own fuse_training (fixture training_24x32_g32):
+    tsdf_est, tsdf_fused (running-mean formula + masking, modules/pipeline.py:104-135,365-405), tsdf_target (second
+    extraction from the GT volume, :309-315) of every frame, and the volumes after the test=False integration --
+    bit for bit, given the reference's own world points."""
+    import numpy as np
+    from online_joint_depthfusion_and_semantic_b200.modules.database import Database, Voxelgrid
+    from online_joint_depthfusion_and_semantic_b200.config import Config
+    g = golden('training_24x32_g32')
+    G, res, h, w = int(g['G']), float(g['res']), 24, 32
+    cfg = fusion_config(h, w, semantic_strategy='gt', use_semantics=False)
+    pipe = Pipeline(cfg).to(DEV)
+    pipe._fusion_network = _ClassicUpdate(res)
+    pipe.train()
+
+    class DS:
+        scenes = ['synth0']
+
+        def get_grid(self, s, init, sem):
+            vg = Voxelgrid(res)
+            vg.from_array(torch.from_numpy(g['gt'].view(np.float16).copy()), np.stack([g['origin'], g['origin'] + G * res], 1))
+            lab = Voxelgrid(res)
+            lab.from_array(torch.zeros(G, G, G, dtype=torch.uint8), vg.bbox)
+            return vg, lab
+    db = Database(DS(), Config(device=DEV, implementation='efficient', init_value=0.1, semantics='class30',
+                               semantic_grid=True, n_classes=30))
+    inner = pipe._extractor.forward
+    for j in range(int(g['n_frames'])):
+        pcl = torch.from_numpy(g['f%d_pcl' % j]).to(DEV)
+        pipe._extractor.forward = lambda *a, _p=pcl, **k: inner(*a, world=_p, **k)       # the reference's BLAS-ordered points
+        batch = {'image': torch.zeros(1, 3, h, w, device=DEV), 'tof_depth': torch.from_numpy(g['f%d_tof_depth' % j]).to(DEV),
+                 'mask': torch.from_numpy(g['f%d_mask' % j]).to(DEV), 'extrinsics': torch.from_numpy(g['f%d_extrinsics' % j]),
+                 'intrinsics': torch.from_numpy(g['f%d_intrinsics' % j]),
+                 'semantic_gt': torch.from_numpy(g['f%d_semantic_gt' % j]).to(DEV), 'frame_id': ['synth0/0/%d' % j]}
+        out = pipe.fuse_training(batch, db, DEV)
+        for k in ('tsdf_est', 'tsdf_fused', 'tsdf_target'):
+            got, want = out[k].detach().cpu().numpy(), g['f%d_%s' % (j, k)]
+            assert got.shape == want.shape, (j, k, got.shape, want.shape)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (j, k, float(np.abs(got - want).max()))
+    torch.cuda.synchronize()
+    assert np.array_equal(db.scenes_est['synth0'].volume.cpu().numpy().view(np.uint16), g['tsdf'])
+    assert np.array_equal(db.fusion_weights['synth0'].cpu().numpy().view(np.uint16), g['wvol'])
+    assert int(db.ids_est['synth0'].volume.count_nonzero()) == 0             # test=False: no semantic update

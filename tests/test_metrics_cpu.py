@@ -131,3 +131,38 @@ def test_database_evaluate_protocol_on_cpu():
     before = db.ids_est['a'].volume.clone()
     db.filter_semantics(5)
     assert np.array_equal(db.ids_est['a'].volume.numpy(), median_filter(before.numpy(), size=5))
+
+
+def _check_against_reference_golden(device):
+    """modules/metrics.py vs the REFERENCE's own utils/metrics.py + scipy median filter (tests/golden/make_golden_metrics.py)."""
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    gold = json.load(open(os.path.join(here, 'metrics.json')))
+    vol = np.load(os.path.join(here, 'metrics_volumes.npz'))
+    for case in range(2):
+        g = gold['case%d' % case]
+        t = lambda k, dt: torch.from_numpy(vol['c%d_%s' % (case, k)].copy()).view(dt).to(device)   # noqa: E731
+        est, gt, w = t('est', torch.float16), t('gt', torch.float16), t('w', torch.float16)
+        ids_est, ids_gt = t('ids_est', torch.uint8), t('ids_gt', torch.uint8)
+        ev = metrics.evaluation(est, gt, w > 0)
+        for k, v in g['evaluation'].items():
+            assert abs(ev[k] - v) <= 2e-6 * max(abs(v), 1e-12), (case, k, ev[k], v)
+        sem, cls_iou = metrics.semantic_evaluation(ids_est, ids_gt, w > 0, g['n_class'])
+        for k, v in g['semantic'].items():
+            assert abs(sem[k] - v) <= 1e-6 * max(abs(v), 1e-12), (case, k, sem[k], v)
+        assert {str(int(k)) for k in cls_iou} == set(g['class_iou'])
+        for k, v in cls_iou.items():
+            assert abs(float(v) - g['class_iou'][str(int(k))]) <= 1e-6
+        med = metrics.median_filter_labels(ids_est, size=5)
+        assert np.array_equal(med.cpu().numpy(), vol['c%d_median5' % case])
+
+
+def test_metrics_vs_reference_golden_cpu():
+    _check_against_reference_golden(torch.device('cpu'))
+
+
+@pytest.mark.gpu
+def test_metrics_vs_reference_golden_gpu():
+    """Row f1 on the device the volumes live on."""
+    _check_against_reference_golden(torch.device('cuda:0'))

@@ -67,3 +67,26 @@ def test_fusionnet_output_matches_reference_values(gold):
     got = y.reshape(-1)[::g['sample_stride']].numpy()
     assert got.shape == ref.shape
     assert np.allclose(got, ref, rtol=1e-5, atol=1e-7)
+
+
+def test_adapnet_output_matches_reference_values(gold):
+    """AdapNet++ stage 2 mirror vs the REFERENCE's own CPU logits (tests/golden/make_golden_nets.py): same seeded
+    parameters (filled in sorted state_dict key order) and input, bottleneck dropout off on both sides."""
+    from online_joint_depthfusion_and_semantic_b200.synthetic import seeded_parameters
+    g = gold['adapnet_stage2_forward']
+    cfg = fusion_config(g['h'], g['w'])
+    cfg.SEMANTIC_2D_MODEL.stage = 2
+    net = seeded_parameters(AdapNet(cfg.SEMANTIC_2D_MODEL), g['param_seed']).eval()
+    net.set_bottleneck_dropout(False)
+    gen = torch.Generator().manual_seed(g['input_seed'])
+    m1, m2 = torch.randn(1, 3, g['h'], g['w'], generator=gen), torch.randn(1, 3, g['h'], g['w'], generator=gen)
+    with torch.no_grad():
+        res, aux1, aux2 = net(m1, m2)
+    assert list(res.shape) == g['logits_shape']
+    scale = g['logits_abs_max']
+    for got, key, stride in ((res, 'sample_values', g['sample_stride']), (aux1, 'aux1_sample', g['sample_stride'] * 7),
+                             (aux2, 'aux2_sample', g['sample_stride'] * 7)):
+        ref = np.asarray(g[key], dtype=np.float32)
+        out = got.reshape(-1)[::stride].numpy()
+        assert out.shape == ref.shape
+        assert float(np.abs(out - ref).max()) <= 1e-5 * scale, key

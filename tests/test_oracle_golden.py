@@ -123,3 +123,17 @@ def test_pipeline_multi_frame_bit_exact(golden, use_ref_pcl):
     else:
         assert mism <= touched // 100, (mism, touched)          # <= 1 % of touched voxels flip
         assert int((ids != g['ids']).sum()) <= touched // 100
+
+
+def test_integrate_zero_over_zero_nan_vs_reference(golden):
+    """0/0 -> NaN is STORED where the reference stores it (modules/integrator.py:82): a reference-generated `updates`
+    dict with zero-weight entries on zero-weight voxels (154 NaN voxels in the fixture)."""
+    g = golden('integrate_updates_nan_g16')
+    tsdf, wvol, ids, sc = g['tsdf0'].copy(), g['wvol0'].copy(), g['ids0'].copy(), g['scores0'].copy()
+    oracle.integrate(g['values'], g['indices'].astype(np.int64), g['weights'], tsdf, wvol, ids=g['semantics'],
+                     scores=g['scores'], ids_vol=ids, scores_vol=sc, do_sem=True)
+    want = g['tsdf1'].view(np.float16)
+    nan_w, nan_g = np.isnan(want), np.isnan(tsdf.view(np.float16))
+    assert int(nan_w.sum()) == 154 and np.array_equal(nan_w, nan_g)
+    assert np.array_equal(tsdf[~nan_g], g['tsdf1'][~nan_w]) and np.array_equal(wvol, g['wvol1'])
+    assert np.array_equal(ids, g['ids1']) and np.array_equal(sc, g['scores1'])

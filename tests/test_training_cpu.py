@@ -75,6 +75,11 @@ def _worker(rank, world, port, frames, acc, out):
         for i, b in enumerate(_rank_data(rank, frames)):
             _, stepped = tr.train_frame(b, None, 'cpu', last=(i == frames - 1))
             steps += stepped
+            if stepped and i == 1:
+                # what the reference loop does around evaluation (train_fusion.py:194): set_to_none=True detaches the
+                # gradient views from the bucket; the trainer must re-attach them or the ranks drift apart silently
+                opt.zero_grad()
+                assert all(p.grad is None for p in pipe._fusion_network.parameters())
         flat = torch.cat([p.detach().reshape(-1) for p in pipe._fusion_network.parameters()])
         gathered = [torch.zeros_like(flat) for _ in range(world)]
         dist.all_gather(gathered, flat)
