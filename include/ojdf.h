@@ -181,7 +181,8 @@ typedef struct ojdf_conv_problem {
     int tap_mask;                   /* 3x3 only: bit t set = tap t (ky*3+kx) contributes; 0 = all nine.  Taps whose shifted
                                      * window lies entirely outside the image are dropped automatically */
 } ojdf_conv_problem;
-/* act additionally accepts 4 = sigmoid.  scratch_dev (optional, scratch_bytes): when the pixel count
+/* act additionally accepts 4 = sigmoid and (tensor-core kernels) 5 = sigmoid(v) * residual (the SSMA gate,
+ * modules/adapnet.py:352; residual_dev required).  scratch_dev (optional, scratch_bytes): when the pixel count
  * alone cannot fill the GPU (AdapNet++'s 15x20 maps) the K loop is split across blocks, partial sums go
  * to the scratch and a second kernel reduces them in a fixed order (deterministic). */
 int ojdf_conv_nhwc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
@@ -215,6 +216,25 @@ int ojdf_conv_tc_pack_weights(const float *w_host, int cin, int cout, int taps, 
 int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
                          int taps, int act, float slope, float out_mul, int npad_req, int flags, float *scratch_dev,
                          size_t scratch_bytes, void *stream);
+/* ---- a17 / a3: the two ends of AdapNet++ that are not tap GEMMs (csrc/ojdf_adapnet_aux.cu) ------
+ * ojdf_adapnet_stem: ResNet-50 conv1 7x7 / 2 / pad 3 (3 -> 64) + BatchNorm(eval, folded into scale/shift) + ReLU +
+ * max-pool 3x3 / 2 / pad 1 (modules/adapnet.py:101,134-137) in one kernel: in_dev (3,H,W) f32 NCHW, weights_dev
+ * (147, 64) f32 = [ci*49 + ky*7 + kx][co] (16-byte aligned), out_dev pixel-major (H/4 * W/4, out_stride) at channel
+ * out_coffset.  Up to 2 problems (the RGB and the depth encoder) per launch; H, W multiples of 4 (AdapNet++ needs 16). */
+typedef struct ojdf_stem_problem {
+    const float *in_dev;
+    const float *weights_dev;
+    const float *scale_dev;
+    const float *shift_dev;
+    float *out_dev;
+    int out_stride, out_coffset;
+} ojdf_stem_problem;
+int ojdf_adapnet_stem(const ojdf_stem_problem *problems_host, int n_problems, int H, int W, void *stream);
+/* softmax over the C class logits of every pixel (pixel-major, `stride` floats per pixel), its maximum -> scores_dev
+ * (npix) f32, its arg-max -> ids_dev (npix) u8, and (optional) the normalised label frame (1 + id) / n_classes ->
+ * sem_frame_dev (npix) f32: modules/pipeline.py:57-58,96,184 in one pass. */
+int ojdf_softmax_max(const float *logits_dev, int stride, int C, int npix, int n_classes, float *scores_dev,
+                     uint8_t *ids_dev, float *sem_frame_dev, void *stream);
 /* nn.AvgPool2d(3, stride 1, padding 1) of VortexPooling (modules/model.py:114-116), C % 4 == 0. */
 int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int W, int C, float *out_dev, int out_stride,
                        void *stream);

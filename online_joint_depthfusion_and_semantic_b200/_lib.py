@@ -44,6 +44,8 @@ _SIGNATURES = {
     'ojdf_gap_bias': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp]),
     'ojdf_nchw_to_nhwc': (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
     'ojdf_nhwc_to_nchw': (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    'ojdf_adapnet_stem': (_i, [_vp, _i, _i, _i, _vp]),
+    'ojdf_softmax_max': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'ojdf_pack_fusion_input': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
 }
 

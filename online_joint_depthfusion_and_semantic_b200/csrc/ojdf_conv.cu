@@ -35,7 +35,7 @@ constexpr int kWChunk4 = kKC * kGroup / 4;           // float4 of weights per ch
 constexpr int kStages = 3;
 constexpr int kMaxBatch = 8;
 
-enum Act { kNone = 0, kRelu = 1, kLeaky = 2, kTanh = 3, kSigmoid = 4 };
+enum Act { kNone = 0, kRelu = 1, kLeaky = 2, kTanh = 3, kSigmoid = 4, kSigmoidMul = 5 };
 
 struct ConvProblem {
     const float *in; const float *weights; const float *scale; const float *shift; float *out;
@@ -228,6 +228,10 @@ conv_reduce_kernel(ConvBatch batch, int npix, int cout, int cpad, int splits, in
     float a = 0.0f;
     for (int s = 0; s < splits; ++s) a += pr.partial[((size_t)s * npix + p) * cpad + c];
     float v = fmaf(a, __ldg(pr.scale + c), __ldg(pr.shift + c));
+    if (act == kSigmoidMul) {                                   // SSMA gate: sigmoid(conv) * gated tensor
+        pr.out[(size_t)p * pr.out_stride + pr.out_coff + c] = pr.residual[(size_t)p * pr.res_stride + c] / (1.0f + expf(-v)) * out_mul;
+        return;
+    }
     if (pr.residual) v += pr.residual[(size_t)p * pr.res_stride + c];
     pr.out[(size_t)p * pr.out_stride + pr.out_coff + c] = activate(v, act, slope) * out_mul;
 }

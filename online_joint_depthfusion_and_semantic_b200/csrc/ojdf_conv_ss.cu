@@ -479,6 +479,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) conv_ss_kernel(const __grid_con
                             case kLeaky: epi_chunk<kLeaky>(v, o, s_ss + n0, rr, nleft, prm.slope, prm.out_mul); break;
                             case kTanh: epi_chunk<kTanh>(v, o, s_ss + n0, rr, nleft, prm.slope, prm.out_mul); break;
                             case kSigmoid: epi_chunk<kSigmoid>(v, o, s_ss + n0, rr, nleft, prm.slope, prm.out_mul); break;
+                            case kSigmoidMul: epi_chunk<kSigmoidMul>(v, o, s_ss + n0, rr, nleft, prm.slope, prm.out_mul); break;
                             default: epi_chunk<kNone>(v, o, s_ss + n0, rr, nleft, prm.slope, prm.out_mul); break;
                         }
                         if (prm.store_mode == 2) {

@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         case kLeaky: epi_chunk<kLeaky>(v, o, s_ss + n0, rrow ? rrow + n0 : nullptr, prm.cout - co_base - n0, prm.slope, prm.out_mul); break;
                         case kTanh: epi_chunk<kTanh>(v, o, s_ss + n0, rrow ? rrow + n0 : nullptr, prm.cout - co_base - n0, prm.slope, prm.out_mul); break;
                         case kSigmoid: epi_chunk<kSigmoid>(v, o, s_ss + n0, rrow ? rrow + n0 : nullptr, prm.cout - co_base - n0, prm.slope, prm.out_mul); break;
+                        case kSigmoidMul: epi_chunk<kSigmoidMul>(v, o, s_ss + n0, rrow ? rrow + n0 : nullptr, prm.cout - co_base - n0, prm.slope, prm.out_mul); break;
                         default: epi_chunk<kNone>(v, o, s_ss + n0, rrow ? rrow + n0 : nullptr, prm.cout - co_base - n0, prm.slope, prm.out_mul); break;
                     }
                     if (prm.store_mode == 2) {
@@ -576,7 +577,7 @@ extern "C" int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int 
                                     float *scratch_dev, size_t scratch_bytes, void *stream)
 {
     if (!problems_host || n_problems < 1 || n_problems > tc::kMaxBatch || cin < 1 || cout < 1 || H < 1 || W < 1 ||
-        H > 32767 || W > 32767 || (taps != 1 && taps != 9) || act < 0 || act > 4)
+        H > 32767 || W > 32767 || (taps != 1 && taps != 9) || act < 0 || act > 5)
         return OJDF_ERR_BADARG;
     {   // 3x3 layers whose halo box fits in shared memory go to the shared-memory-operand kernel (ojdf_conv_ss.cu), the
         // rest stays here.  OJDF_CONV_KERNEL=ts / flag 65536: always this file's kernel; =ss / flag 32768: always the other.

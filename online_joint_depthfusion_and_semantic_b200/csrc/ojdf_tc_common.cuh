@@ -24,7 +24,7 @@ constexpr int kAS = 6;                   // most A stages in TMEM (64 columns ea
 constexpr int kMaxSrc = 4, kMaxB = 8;
 constexpr int kSlabBytes = 128 * 128;    // staging slab: 128 pixels x 32 channels
 
-enum Act { kNone = 0, kRelu = 1, kLeaky = 2, kTanh = 3, kSigmoid = 4 };
+enum Act { kNone = 0, kRelu = 1, kLeaky = 2, kTanh = 3, kSigmoid = 4, kSigmoidMul = 5 };   // 5: sigmoid(v) * residual (SSMA gate)
 
 struct Problem {
     const float *weights, *scale, *shift;
@@ -199,11 +199,12 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[16], float (&o)[16
     for (int c = 0; c < 16; ++c) {
         const float2 p = ss[c];
         float r = fmaf(__uint_as_float(v[c]), p.x, p.y);
-        if (res && c < ncols) r += res[c];
+        if (ACT != kSigmoidMul && res && c < ncols) r += res[c];
         if (ACT == kRelu) r = fmaxf(r, 0.0f);
         if (ACT == kLeaky) r = r > 0.0f ? r : r * slope;
         if (ACT == kTanh) r = tanhf(r);
         if (ACT == kSigmoid) r = 1.0f / (1.0f + expf(-r));
+        if (ACT == kSigmoidMul) r = (res && c < ncols) ? res[c] / (1.0f + expf(-r)) : 0.0f;
         o[c] = r * out_mul;
     }
 }

@@ -263,7 +263,7 @@ class AdapNet(EngineOwner, nn.Module):
                 m.dropout = bool(enabled) and m.dropout_default
         return self
 
-    def _whole(self, mod1, mod2):
+    def _whole_engine(self, mod1):
         from .adapnet_engine import AdapNetEngine
         h, w = mod1.shape[-2:]
         self._hook_load_state_dict()
@@ -271,11 +271,24 @@ class AdapNet(EngineOwner, nn.Module):
         e = self._full_engine
         if e is None or (e.h, e.w) != (h, w) or e.device != mod1.device:
             e = self._full_engine = AdapNetEngine(self, h, w, mod1.device)
-        return e.forward(mod1, mod2)
+        return e
+
+    def _whole(self, mod1, mod2):
+        return self._whole_engine(mod1).forward(mod1, mod2)
+
+    def whole_engine_ready(self, mod1):
+        from .fusion_engine import conv_mode
+        return self.engine_ready(mod1) and self.whole_engine and conv_mode() == 'tc' and mod1.shape[0] == 1
+
+    def segment(self, mod1, mod2=None):
+        """(scores f32, ids u8, (1 + id) / n_classes f32), each (1,h,w): the per-pixel maximum / arg-max of
+        softmax(main head) -- what the fusion pipeline consumes (modules/pipeline.py:57-58,184) -- computed by the
+        launch plan plus one fused softmax-max kernel.  Only with whole_engine_ready(); forward() is the general path."""
+        assert self.whole_engine_ready(mod1)
+        return self._whole_engine(mod1).segment(mod1, mod2)
 
     def forward(self, mod1, mod2=None):
-        from .fusion_engine import conv_mode
-        if self.engine_ready(mod1) and self.whole_engine and conv_mode() == 'tc' and mod1.shape[0] == 1:
+        if self.whole_engine_ready(mod1):
             return self._whole(mod1, mod2)
         if self.engine_ready(mod1):
             # front (conv1..layer3[0]) on the library, the 15x20 tail + eASPP on libojdf's kernels

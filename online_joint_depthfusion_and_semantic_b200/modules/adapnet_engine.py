@@ -30,7 +30,15 @@ from torch.nn import functional as F
 
 from .. import _lib
 
+import ctypes as C
+
 from .fusion_engine import ConvProblem, _Conv as _ConvBase, _pad4, conv_mode
+
+
+class StemProblem(C.Structure):
+    """include/ojdf.h: ojdf_stem_problem."""
+    _fields_ = [('in_dev', C.c_void_p), ('weights_dev', C.c_void_p), ('scale_dev', C.c_void_p), ('shift_dev', C.c_void_p),
+                ('out_dev', C.c_void_p), ('out_stride', C.c_int), ('out_coffset', C.c_int)]
 
 _TAIL_PIXELS = 300          # 15 x 20: four 128-pixel M-tiles per problem
 
@@ -312,6 +320,18 @@ class AdapNetEngine:
 
         # ---- encoders: stem (library) -> layer1 -> skip2 -> layer2 -> skip1 -> layer3[0] -> tail engine
         self.S0 = [z(N4, 64) for _ in range(n)]
+        self.stem = []                                          # (weights (147, 64), scale, shift) of conv1 + bn1 per encoder
+        for e in encs:
+            r = e.res_n50_enc
+            assert tuple(r.conv1.kernel_size) == (7, 7) and tuple(r.conv1.stride) == (2, 2) and tuple(r.conv1.padding) == (3, 3)
+            assert r.conv1.in_channels == 3 and r.conv1.out_channels == 64 and r.conv1.bias is None
+            wst = r.conv1.weight.detach().double().cpu().permute(1, 2, 3, 0).reshape(147, 64).float().contiguous().to(dev)
+            sc = r.bn1.weight.detach().double().cpu() / torch.sqrt(r.bn1.running_var.detach().double().cpu() + r.bn1.eps)
+            sh = r.bn1.bias.detach().double().cpu() - r.bn1.running_mean.detach().double().cpu() * sc
+            self.stem.append((wst, sc.float().contiguous().to(dev), sh.float().contiguous().to(dev)))
+        self.seg_scores = torch.empty(1, h, w, dtype=torch.float32, device=dev)
+        self.seg_ids = torch.empty(1, h, w, dtype=torch.uint8, device=dev)
+        self.seg_frame = torch.empty(1, h, w, dtype=torch.float32, device=dev)
         self.FX = z(N16, n * 256)                              # eASPP outputs of all encoders side by side
         self.tail = EncoderTailEngine(encs, aspps, H16, W16, dev, out_buf=self.FX)
         cur, cs = self.S0, 64
@@ -343,12 +363,12 @@ class AdapNetEngine:
         # ---- SSMA fusion of the two modalities (stage 2): cat -> 3x3 relu -> 3x3 sigmoid -> gate -> 3x3 + BN
         def ssma(m, cat, N, H, W, feat):
             red = m.link[0].out_channels
-            l0, l1 = mk(m.link[0], None, 'relu', H, W, 1), mk(m.link[2], None, 'sigmoid', H, W, 1)
+            # the gate multiplies the concatenated features (modules/adapnet.py:352): epilogue mode sigmoid(v) * residual
+            l0, l1 = mk(m.link[0], None, 'relu', H, W, 1), mk(m.link[2], None, 'sigmoid_mul', H, W, 1)
             fin = mk(m.final_conv[0], m.final_conv[1], 'none', H, W, 1)
             G, GATE, out = z(N, _pad4(red)), z(N, 2 * feat), z(N, feat)
             conv_step([(l0, l0.problem(cat, 2 * feat, G, _pad4(red)))], H, W)
-            conv_step([(l1, l1.problem(G, _pad4(red), GATE, 2 * feat))], H, W)
-            plan.append(('mul', GATE, cat))
+            conv_step([(l1, l1.problem(G, _pad4(red), GATE, 2 * feat, residual=cat, residual_stride=2 * feat))], H, W)
             conv_step([(fin, fin.problem(GATE, 2 * feat, out, feat))], H, W)
             return out
 
@@ -415,11 +435,11 @@ class AdapNetEngine:
         aux = {}
         with torch.cuda.device(dev), _lib.timed('adapnet_engine', dev):
             st = _lib.stream_ptr(dev)
-            encs = [net.encoder_mod1] + ([net.encoder_mod2] if self.stage2 else [])
-            for e, (enc, x) in enumerate(zip(encs, [mod1, mod2][:self.n])):
-                r = enc.res_n50_enc
-                y = r.maxpool(r.relu(r.bn1(r.conv1(x.float())))).contiguous()
-                _lib.check(L.ojdf_nchw_to_nhwc(y.data_ptr(), 64, H4 * W4, self.S0[e].data_ptr(), 64, 0, st))
+            # stem: conv1 7x7/2 + BatchNorm + ReLU + max-pool 3x3/2 of every encoder in one launch, pixel-major out
+            xs = [x.detach().float().contiguous() for x in [mod1, mod2][:self.n]]
+            arr = (StemProblem * self.n)(*[StemProblem(xs[e].data_ptr(), self.stem[e][0].data_ptr(), self.stem[e][1].data_ptr(),
+                                                       self.stem[e][2].data_ptr(), self.S0[e].data_ptr(), 64, 0) for e in range(self.n)])
+            _lib.check(L.ojdf_adapnet_stem(arr, self.n, self.h, self.w, st))
             for step in self.plan:
                 kind = step[0]
                 if kind == 'conv':
@@ -431,8 +451,6 @@ class AdapNetEngine:
                 elif kind == 'dropout':
                     for t in step[1]:                            # reference quirk: active in eval mode
                         t.copy_(F.dropout(t, p=0.5, training=True))
-                elif kind == 'mul':
-                    step[1].mul_(step[2])                        # gate * concatenated features (modules/adapnet.py:352)
                 elif kind == 'join1':
                     x = self._nchw(self.J1, H8, W8, 0, 256)      # relu(bn(deconv1(.))), written by the phase convolutions
                     aux['y1'] = d._aux(x, d.aux_conv1, d.aux_conv1_bn, 8) if net.aux_heads else None
@@ -443,6 +461,17 @@ class AdapNetEngine:
                     self._join(x, self.skip2, d.fuse_conv2, self.J2, H4, W4)
             res = self._nchw(self.LG, self.h, self.w, 0, int(d.n_classes))     # (1, C, h, w) view of the pixel-major logits
         return [res, aux['y1'], aux['y2']]
+
+    def segment(self, mod1, mod2=None):
+        """forward() + the per-pixel softmax maximum / arg-max of the main head (modules/pipeline.py:57-58,184) in one
+        extra launch: returns (scores (1,h,w) f32, ids (1,h,w) u8, (1 + id) / n_classes (1,h,w) f32) -- buffers owned by the
+        engine, overwritten by the next call."""
+        self.forward(mod1, mod2)
+        C_ = int(self.net.decoder.n_classes)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ojdf_softmax_max(self.LG.data_ptr(), self.Cp, C_, self.h * self.w, C_, self.seg_scores.data_ptr(),
+                                                   self.seg_ids.data_ptr(), self.seg_frame.data_ptr(), _lib.stream_ptr(self.device)))
+        return self.seg_scores, self.seg_ids, self.seg_frame
 
     def _join(self, x, skip, conv, J, H, W):
         """Decoder._join (modules/adapnet.py:305-315): [x | gate * skip] into the 280-channel buffer J."""

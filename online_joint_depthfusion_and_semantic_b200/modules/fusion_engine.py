@@ -30,7 +30,7 @@ from torch import nn
 from .. import _lib
 
 _GROUP = 20
-_ACT = {'none': 0, 'relu': 1, 'lrelu': 2, 'tanh': 3, 'sigmoid': 4}
+_ACT = {'none': 0, 'relu': 1, 'lrelu': 2, 'tanh': 3, 'sigmoid': 4, 'sigmoid_mul': 5}
 
 
 def _pad4(c):

@@ -51,6 +51,8 @@ class Pipeline(nn.Module):
         self.plan_ahead = True               # issue the geometry half of the integration on a side stream, early
         self._seg_graph = None
         self._seg_graph_token = (None, None)
+        self._seg_graph_fn = None
+        self._sem_frame = None
 
     def train(self, mode=True):
         self._seg_graph = None               # captured graphs hold parameter addresses / modes
@@ -76,6 +78,37 @@ class Pipeline(nn.Module):
             logits = net(image, aux.repeat(1, 3, 1, 1).float())[0]
         return torch.softmax(logits, dim=1).permute(0, 2, 3, 1)
 
+    def _seg_inputs(self, image, aux):
+        image = (image / 255.0).float()                                # quirk: /255 after mean/std normalisation
+        if self.config.SEMANTIC_2D_MODEL.stage == 1:
+            return (image if aux is None else aux.repeat(1, 3, 1, 1).float()), None
+        return image, aux.repeat(1, 3, 1, 1).float()
+
+    def _segment_fast(self, image, aux):
+        """(scores, ids u8, label frame): AdapNet++ launch plan + fused softmax / max / arg-max kernel."""
+        net = self._semantic_2d_network
+        net.aux_heads = False
+        return net.segment(*self._seg_inputs(image, aux))
+
+    def _graphed(self, fn, image, aux):
+        """Replay `fn(image, aux)` as a CUDA graph.  The captured graph replays kernels that point into the AdapNet++ launch
+        plan: it is only valid while that very plan object is alive and its parameters are unchanged (eval() / .to() /
+        load_state_dict() / in-place writes on the network drop the plan, modules/_engine_cache.py)."""
+        net = self._semantic_2d_network
+        net._hook_load_state_dict()
+        net.engines_current()
+        if self._seg_graph is not None and (self._seg_graph_fn != fn or
+                                            any(a is not b for a, b in zip(net.engine_token(), self._seg_graph_token))):
+            self._seg_graph = None
+        fresh = self._seg_graph is None
+        if fresh:
+            self._seg_graph = GraphedCall(lambda *a: fn(a[0], a[1] if len(a) > 1 else None))
+            self._seg_graph_fn = fn
+        out = self._seg_graph(image) if aux is None else self._seg_graph(image, aux)
+        if fresh:
+            self._seg_graph_token = net.engine_token()
+        return out
+
     def _segmentation(self, data):
         key = self.config.DATA.input
         image = data['image'].to(self.device)
@@ -84,28 +117,25 @@ class Pipeline(nn.Module):
         graphable = (self.use_cuda_graphs and image.is_cuda and not torch.is_grad_enabled() and not net.training)
         if not graphable:
             return self._segmentation_eager(image, aux)
-        # The captured graph replays kernels that point into the AdapNet++ launch plan: it is only valid while that very
-        # plan object is alive and its parameters are unchanged (eval() / .to() / load_state_dict() / in-place writes on
-        # the network drop the plan, modules/_engine_cache.py).
-        net._hook_load_state_dict()
-        net.engines_current()
-        if self._seg_graph is not None and any(a is not b for a, b in zip(net.engine_token(), self._seg_graph_token)):
-            self._seg_graph = None
-        fresh = self._seg_graph is None
-        if fresh:
-            self._seg_graph = GraphedCall(lambda *a: self._segmentation_eager(a[0], a[1] if len(a) > 1 else None))
-        out = self._seg_graph(image) if aux is None else self._seg_graph(image, aux)
-        if fresh:
-            self._seg_graph_token = net.engine_token()
-        return out
+        return self._graphed(self._segmentation_eager, image, aux)
 
     def _semantic_frame(self, batch, as_uint8):
         """(scores f32, ids) per pixel, or (None, None): modules/pipeline.py:181-193,277-292."""
         if not self.config.DATA.semantics:
             return None, None
         strategy = self.config.DATA.semantic_strategy
+        self._sem_frame = None
         if strategy == 'predict':
+            net = self._semantic_2d_network
+            image = batch['image'].to(self.device)
+            key = self.config.DATA.input
+            aux = None if key == 'image' else batch[key].to(self.device)
+            fast = not torch.is_grad_enabled() and net.whole_engine_ready(image)
             with torch.no_grad(), _lib.timed('adapnet', self.device):
+                if fast:
+                    fn = self._segment_fast
+                    scores, ids, self._sem_frame = (self._graphed(fn, image, aux) if self.use_cuda_graphs else fn(image, aux))
+                    return scores, (ids if as_uint8 else ids.long())
                 scores, ids = self._segmentation(batch).max(dim=-1)
         elif strategy == 'gt':
             ids = batch['semantic_gt'].to(self.device).long()
@@ -149,7 +179,7 @@ class Pipeline(nn.Module):
         sem = None
         if self.config.FUSION_MODEL.use_semantics:
             assert sem_ids is not None
-            sem = (1 + sem_ids.reshape(b, h, w).float()) / self.n_classes
+            sem = self._sem_frame if self._sem_frame is not None else (1 + sem_ids.reshape(b, h, w).float()) / self.n_classes
         return net.engine_for(h, w, frame.device).pack_target(frame.reshape(b, h, w), sem)
 
     # ---- a12: loss tensors (modules/pipeline.py:104-135) ------------------------------------------

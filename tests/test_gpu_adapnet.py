@@ -56,3 +56,28 @@ def test_dropout_quirk_stays_random_with_engine():
     with torch.no_grad():
         a, b = net(x1, x2)[0].clone(), net(x1, x2)[0].clone()
     assert float((a - b).abs().max()) > 0          # eval-time-active dropout, as in the reference
+
+
+@pytest.mark.parametrize('stage,h,w', [(2, 240, 320), (1, 64, 96)])
+def test_segment_scores_ids_vs_torch_softmax_max(stage, h, w):
+    """Row a3: `AdapNet.segment` (launch plan + own stem kernel + fused softmax / max / arg-max kernel) against
+    torch.softmax(logits, 1).max(1) of the plain fp32 forward (modules/pipeline.py:57-58,184)."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = _net(stage)
+    g = torch.Generator().manual_seed(5)
+    x1, x2 = torch.randn(1, 3, h, w, generator=g).to(DEV), torch.randn(1, 3, h, w, generator=g).to(DEV)
+    args = (x1, x2) if stage == 2 else (x1,)
+    with torch.no_grad():
+        net.use_engine = False
+        probs = torch.softmax(net(*args)[0], dim=1)
+        ref_scores, ref_ids = probs.max(dim=1)
+        net.use_engine = True
+        net.aux_heads = False
+        scores, ids, frame = net.segment(*args)
+        torch.cuda.synchronize()
+    assert scores.shape == (1, h, w) and ids.dtype == torch.uint8
+    assert float((ids.long() == ref_ids).float().mean()) > 0.999
+    same = ids.long() == ref_ids
+    assert float((scores[same] - ref_scores[same]).abs().max()) <= 1e-4 * float(ref_scores.max())
+    assert torch.allclose(frame, (1 + ids.float()) / net.decoder.n_classes, rtol=1e-6, atol=0)

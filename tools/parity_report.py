@@ -76,7 +76,8 @@ def parity(frames=100, h=240, w=320, grid=256, cuda=True, strategy='predict'):
     if pipe_c._semantic_2d_network is not None:
         pipe_c._semantic_2d_network.set_bottleneck_dropout(False)       # deterministic on both sides
     fuse_cpu_port(pipe_c, db_c, host_frames)
-    out['cpu_port'] = report(db_c)
+    if not cuda:
+        out['cpu_port'] = report(db_c)
     if cuda:
         dev = torch.device('cuda', 0)
         _, pipe_g, db_g, _ = bench.build_world(dev, 0, h=h, w=w, grid=grid, scenes_per_rank=1, frames=1, strategy=strategy)
@@ -86,7 +87,7 @@ def parity(frames=100, h=240, w=320, grid=256, cuda=True, strategy='predict'):
             for hb in host_frames:
                 pipe_g.fuse(bench.to_device_frame(hb, dev), db_g, dev)
         torch.cuda.synchronize()
-        # raw volume agreement before any filtering.  The two paths differ by ~1e-6 in the network outputs (3xTF32 vs
+        # raw volume agreement BEFORE any filtering (report() filters in place).  The two paths differ by ~1e-6 in the network outputs (3xTF32 vs
         # fp32 summation order); over `frames` frames the fp16 running means round differently now and then, so many
         # voxels end up a few fp16 ulps apart -- what matters is how far, and that the metrics do not move.
         s = db_g.scenes[0]
@@ -104,6 +105,7 @@ def parity(frames=100, h=240, w=320, grid=256, cuda=True, strategy='predict'):
                           'tsdf_mean_abs_diff': float(d.mean()) if touched else 0.0,
                           'label_voxels_differing': int((i_g != i_c)[touched_m].sum()),
                           'label_agreement': float((i_g == i_c)[touched_m].float().mean()) if touched else 1.0}
+        out['cpu_port'] = report(db_c)
         out['cuda'] = report(db_g)
         out['abs_diff'] = {k: abs(out['cuda'][k] - out['cpu_port'][k]) for k in out['cuda']}
         out['max_abs_diff_points'] = 100.0 * max(out['abs_diff'][k] for k in ('iou', 'acc', 'f1', 'Mean IoU', 'Mean Acc')
