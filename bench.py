@@ -429,12 +429,110 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_train(args):
+    """--mode train: config 5 of BASELINE.json on synthetic frames -- every rank streams its own scenes through
+    Pipeline.fuse_training (frozen AdapNet++ on the own kernels, Extractor x2, FusionNet_v3 with autograd, FusionLoss,
+    Integrator test=False), gradients accumulate for 8 frames with the reference's per-iteration clip
+    (train_fusion.py:166-189), then ONE NCCL all-reduce of the flat FusionNet gradient bucket and an RMSprop step.
+    A step = one frame; value = frames/s over all ranks; the all-reduce is timed with CUDA events."""
+    from online_joint_depthfusion_and_semantic_b200.training import FusionLoss, PolynomialLR, ShardedFusionTrainer
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --mode train needs CUDA devices')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+    cfg, pipe, db, host_frames = build_world(device, rank, scenes_per_rank=2, frames=8)
+    pipe.train()
+    pipe._semantic_2d_network.eval()                         # frozen, as train_fusion.py:90-94
+    for p_ in pipe._semantic_2d_network.parameters():
+        p_.requires_grad_(False)
+    opt = torch.optim.RMSprop(pipe._fusion_network.parameters(), lr=1e-5, momentum=0.9, weight_decay=0.01, eps=1e-9)
+    trainer = ShardedFusionTrainer(pipe, opt, PolynomialLR(opt, max_iter=50000), FusionLoss(), accumulation_steps=8, clipping=True)
+    trainer.time_collective = True
+    trainer.broadcast_parameters()
+    dev_frames = [to_device_frame(hb, device) for hb in host_frames]
+    nf = len(dev_frames)
+
+    def step(i):
+        b = dict(dev_frames[i % nf])
+        b['tof_depth'] = b['tof_depth'].clone()              # fuse_training squeezes its input in place
+        loss, _ = trainer.train_frame(b, db, device)
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps = max(8, args.steps // 8 * 8) if args.steps < 200 else 64          # whole accumulation windows
+    for i in range(max(8, args.warmup // 8 * 8)):
+        step(i)
+    barrier()
+    trainer.collective_events.clear()
+    with ClockSampler(local) as sampler:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        loss = None
+        for i in range(steps):
+            loss = step(i)
+        b.record()
+        barrier()
+    ms = torch.tensor([a.elapsed_time(b)], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ar = [x.elapsed_time(y) * 1e3 for x, y in trainer.collective_events]
+    # the collective alone: the same 2.29 MB bucket all-reduced back to back after a barrier (the in-loop figure above
+    # also contains the wait for the slowest rank to reach the collective)
+    iso = None
+    if dist is not None:
+        bucket = trainer._flat_bucket().clone()
+        for _ in range(5):
+            dist.all_reduce(bucket)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            dist.all_reduce(bucket)
+        e1.record()
+        torch.cuda.synchronize()
+        iso_t = torch.tensor([e0.elapsed_time(e1) * 1e3 / 50], device=device, dtype=torch.float64)
+        dist.all_reduce(iso_t, op=dist.ReduceOp.MAX)
+        iso = float(iso_t.item())
+    nparam = sum(p_.numel() for p_ in trainer.params)
+    if rank == 0:
+        print(json.dumps({
+            'mode': 'train', 'metric': 'online_training_frames_per_second_240x320_into_256cube', 'value': world * steps / (float(ms.item()) / 1e3),
+            'unit': 'frames/s', 'n_gpus': world, 'steps': steps, 'warmup': 8, 'ms_per_step': float(ms.item()) / steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'fp32 (FusionNet forward/backward: PyTorch autograd, cuDNN, TF32 off); frozen AdapNet++ + extract + integrate: own kernels',
+            'data': 'synthetic', 'config': {'workload': 'configs[4]: fuse_training on scene-sharded streams, 8-frame accumulation, '
+                                                       'one NCCL all-reduce of the flat FusionNet gradient per optimiser step',
+                                            'frame': [H, W], 'grid': GRID, 'accumulation_steps': 8},
+            'allreduce': {'bytes': 4 * nparam, 'calls': len(ar), 'us_in_loop_mean_incl_rank_skew': float(np.mean(ar)) if ar else None,
+                          'us_in_loop_min': float(np.min(ar)) if ar else None, 'us_isolated_back_to_back': iso,
+                          'bus_GBps_isolated': (4 * nparam * 2 * (world - 1) / world / (iso * 1e-6) / 1e9) if iso else None},
+            'loss': float(loss), 'clocks': sampler.summary()}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
+    ap.add_argument('--mode', default='fuse', choices=['fuse', 'train'],
+                    help="fuse (default): the headline inference metric; train: BASELINE.json configs[4], online training with the NCCL gradient all-reduce")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--parity', type=int, default=0, metavar='FRAMES',
                     help='also fuse FRAMES frames through the CUDA path and the CPU port and report the metric parity (N=1)')
@@ -445,6 +543,8 @@ def main():
         args.warmup = 3
     if args.impl == 'reference':
         run_reference(args)
+    elif args.mode == 'train':
+        run_train(args)
     else:
         run_own(args)
 

@@ -130,9 +130,8 @@ class Pipeline(nn.Module):
             image = batch['image'].to(self.device)
             key = self.config.DATA.input
             aux = None if key == 'image' else batch[key].to(self.device)
-            fast = not torch.is_grad_enabled() and net.whole_engine_ready(image)
-            with torch.no_grad(), _lib.timed('adapnet', self.device):
-                if fast:
+            with torch.no_grad(), _lib.timed('adapnet', self.device):      # AdapNet++ is frozen on the fusion path
+                if net.whole_engine_ready(image):
                     fn = self._segment_fast
                     scores, ids, self._sem_frame = (self._graphed(fn, image, aux) if self.use_cuda_graphs else fn(image, aux))
                     return scores, (ids if as_uint8 else ids.long())

@@ -68,6 +68,8 @@ class ShardedFusionTrainer:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self._bucket = None
         self.iteration = 0
+        self.time_collective = False                             # bench: CUDA events around every all-reduce
+        self.collective_events = []
 
     def _flat_bucket(self):
         """All FusionNet gradients as views into one contiguous buffer -> a single collective.
@@ -119,7 +121,14 @@ class ShardedFusionTrainer:
         if self.iteration % self.accumulation_steps == 0 or last:
             bucket = self._flat_bucket()                         # re-attach anything that replaced a gradient view
             if self.world > 1:
+                ev = None
+                if self.time_collective and bucket.is_cuda:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
                 dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group)
+                if ev is not None:
+                    ev[1].record()
+                    self.collective_events.append(ev)
                 bucket.div_(self.world)
             self.optimizer.step()
             bucket.zero_()                                       # == optimizer.zero_grad() with the views kept
