@@ -54,6 +54,18 @@ TRAFFIC = {'fusionnet': None, 'integrate': None, 'extract': None}
 SCENES_PER_RANK, FRAMES_PER_SCENE = 4, 6
 METRIC = 'fused_frames_per_second_240x320_into_256cube'
 WORKLOAD = 'configs[1]: synthetic Replica-like room, 256^3 grid, 240x320 RGB-D, AdapNet++(stage2,30cls)+FusionNet_v3(sem)+extract+integrate'
+PRECISION = 'parity'
+
+
+def select_config(name):
+    """'headline' = BASELINE.json configs[1] (the metric's configuration, default); 'fast480' = configs[2]: 480x640 frames
+    into a 512^3 grid with the tensor-core convolutions in the `fast` precision mode (1xTF32 instead of 3xTF32)."""
+    global H, W, GRID, SCENES_PER_RANK, METRIC, WORKLOAD, PRECISION
+    if name == 'fast480':
+        H, W, GRID, SCENES_PER_RANK, PRECISION = 480, 640, 512, 2, 'fast'
+        METRIC = 'fused_frames_per_second_480x640_into_512cube_fast_precision'
+        WORKLOAD = ('configs[2]: synthetic Replica-like room, 512^3 grid, 480x640 RGB-D, AdapNet++(stage2,30cls)+FusionNet_v3(sem) '
+                    'with 1xTF32 tensor-core convolutions (precision mode fast) + extract + integrate')
 
 
 def peaks():
@@ -128,8 +140,10 @@ class SceneSet:
         return (g, l)
 
 
-def build_world(device, rank, h=H, w=W, grid=GRID, scenes_per_rank=SCENES_PER_RANK, frames=FRAMES_PER_SCENE,
+def build_world(device, rank, h=None, w=None, grid=None, scenes_per_rank=None, frames=FRAMES_PER_SCENE,
                 render_device=None, strategy='predict'):
+    h, w, grid = h or H, w or W, grid or GRID                # the selected configuration (select_config) unless given
+    scenes_per_rank = scenes_per_rank or SCENES_PER_RANK
     from online_joint_depthfusion_and_semantic_b200.config import Config
     from online_joint_depthfusion_and_semantic_b200.modules.database import Database
     from online_joint_depthfusion_and_semantic_b200.modules.pipeline import Pipeline
@@ -205,6 +219,7 @@ def run_own(args):
     _lib.lib()
 
     cfg, pipe, db, host_frames = build_world(device, rank)
+    pipe.set_precision(PRECISION)
     tap = ResultTap(pipe)
     dev_frames = [to_device_frame(hb, device) for hb in host_frames]
     torch.cuda.synchronize()
@@ -282,7 +297,8 @@ def run_own(args):
     roof_int = {'kernel': 'ojdf_integrate_plan (count + offsets + scatter; side stream, overlaps the networks) + '
                           'ojdf_integrate_apply (apply_short + apply_long; the only part after FusionNet)', 'bound': 'hbm',
                 'achieved': int_bytes / (int_total * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
-                'frac': int_bytes / (int_total * 1e-3) / 1e9 / peak, 'traffic': TRAFFIC.get('integrate'), 'peak_source': peak_src,
+                'frac': int_bytes / (int_total * 1e-3) / 1e9 / peak, 'traffic': TRAFFIC.get('integrate') if PRECISION == 'parity' else None,
+                'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': int_bytes, 'ms_per_launch': float(int_total),
                 'ms_plan_side_stream': float(plan_ms), 'ms_apply_critical_path': float(int_ms)}
     ext_total = ext_ms + rays_ms
@@ -303,7 +319,9 @@ def run_own(args):
     line = {
         'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64 ray geometry / f32 accumulation / f16+u8 volumes; FusionNet + AdapNet++ convolutions: fp32 via 3xTF32 tcgen05 (own kernels, ~1e-6 of fp32); AdapNet++ 7x7 stem + max-pool: f32 library (TF32 off)',
+        'dtype': 'f64 ray geometry / f32 accumulation / f16+u8 volumes; FusionNet + AdapNet++ convolutions: '
+                 + ('fp32 via 3xTF32 tcgen05 (own kernels, ~1e-6 of fp32)' if PRECISION == 'parity' else '1xTF32 tcgen05 (own kernels, precision mode fast, ~1e-3)')
+                 + '; AdapNet++ 7x7 stem: fp32 FMA (own kernel)',
         'data': 'synthetic (analytic SDF room, seeded; random-init networks seed 1911)',
         'config': {'workload': WORKLOAD, 'frame': [H, W], 'grid': GRID, 'scenes_per_gpu': SCENES_PER_RANK,
                    'sharding': 'scenes one-per-rank, no collective',
@@ -533,6 +551,8 @@ def main():
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--mode', default='fuse', choices=['fuse', 'train'],
                     help="fuse (default): the headline inference metric; train: BASELINE.json configs[4], online training with the NCCL gradient all-reduce")
+    ap.add_argument('--config', default='headline', choices=['headline', 'fast480'],
+                    help='headline: BASELINE.json configs[1] (default); fast480: configs[2], 480x640 -> 512^3, precision mode fast')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--parity', type=int, default=0, metavar='FRAMES',
                     help='also fuse FRAMES frames through the CUDA path and the CPU port and report the metric parity (N=1)')
@@ -541,6 +561,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    select_config(args.config)
     if args.impl == 'reference':
         run_reference(args)
     elif args.mode == 'train':

@@ -207,7 +207,10 @@ int ojdf_conv_nhwc_batched(const ojdf_conv_problem *problems_host, int n_problem
  *     store path is taken); experiments: 2 = one M-tile per group, 4 = never use halo boxes, 8 = per-thread
  *     stores, 16..2048 and bits 12-15 = timing probes (see the source), 4096 = never split the K loop;
  *   - scratch_dev (optional, scratch_bytes): lets the K loop be split over several CTAs when the feature map
- *     is too small to fill the SMs; partial sums are reduced in a fixed order by a second kernel (deterministic). */
+ *     is too small to fill the SMs; partial sums are reduced in a fixed order by a second kernel (deterministic).
+ *     flags 16384 (experimental, slower today): the CTA that delivers the last K slice of a tile reduces it inside the
+ *     kernel; the first 16 KB of the scratch are then per-tile slice counters that must be ZERO before the first launch
+ *     (every launch leaves them zero). */
 int ojdf_conv_tc_layout(int cout, int npad_req, int *npad, int *groups);
 size_t ojdf_conv_tc_weight_floats(int cin, int cout, int taps, int npad_req);
 /* w_host: (cout, cin, taps) fp32 as in nn.Conv2d.weight (tap = ky*3 + kx); packed_host:

@@ -51,6 +51,7 @@ stem_kernel(StemBatch batch, int H, int W)
         reinterpret_cast<float4 *>(s_w)[i] = __ldg(reinterpret_cast<const float4 *>(pr.w) + i);
     __syncthreads();
     // conv tile: work item = (position, group of 16 output channels)
+#pragma unroll 1
     for (int item = threadIdx.x; item < kCT_H * kCT_W * 4; item += kStemThreads) {
         const int pos = item >> 2, g = item & 3;
         const int r = pos / kCT_W, c = pos % kCT_W;
@@ -64,7 +65,9 @@ stem_kernel(StemBatch batch, int H, int W)
         float acc[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+#pragma unroll 1
         for (int ci = 0; ci < 3; ++ci)
+#pragma unroll 1                                           // (fully unrolled this nest is 650 KB of code: it lives in L2, not in the I-cache)
             for (int ky = 0; ky < 7; ++ky) {
                 const float *irow = s_in + (ci * kIT_H + 2 * r + ky) * kIT_W + 2 * c;
                 const float *wrow = s_w + (size_t)((ci * 7 + ky) * 7) * kStemCout + g * 16;

@@ -48,7 +48,7 @@ struct SsParams {
     CUtensorMap out_map[kMaxBatch];
     Problem p[kMaxBatch];
     int H, W, cin, cout, taps, act, npad, groups, nkc, tiles_x, tiles_y, nprob;
-    int mt, nacc, hd, halo, fused, acc_cols;
+    int mt, nacc, hd, halo, fused, acc_cols, fast;
     int src_stages, b_stages, src_bytes, box_bytes, bwid, stg_slabs, store_mode, ksplit, cpad, dbg, ni;
     int tap_mask[kMaxBatch];
     float slope, out_mul;
@@ -106,8 +106,12 @@ __device__ __forceinline__ void issue_k(uint32_t acc, uint32_t a, uint32_t lo_de
     }
 }
 __device__ __forceinline__ void issue_tile(bool fused, int ksteps, uint32_t acc, uint32_t a, uint32_t lo_delta, uint32_t b, uint32_t wl_delta,
-                                           uint32_t AH, uint32_t BH, uint32_t idw, uint32_t idn, uint32_t accum)
+                                           uint32_t AH, uint32_t BH, uint32_t idw, uint32_t idn, uint32_t accum, bool fast = false)
 {
+    if (fast) {                                                 // 1xTF32: hi * W_hi only (precision mode `fast`)
+        for (int k = 0; k < ksteps; ++k) umma_ss2(acc, a + 2 * k, AH, b + 2 * k, BH, idn, k ? 1u : accum);
+        return;
+    }
     if (fused) {
         switch (ksteps) {
             case 4: issue_k<4, true>(acc, a, lo_delta, b, wl_delta, AH, BH, idw, idn, accum); break;
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) conv_ss_kernel(const __grid_con
         const uint32_t a_base = (src0 >> 4) | (1u << 16), b_base = (bst0 >> 4) | (1u << 16);
         const uint32_t lo_delta = (lo0 - src0) >> 4;             // raw box -> its lo copy
         const uint32_t a_step = (uint32_t)prm.src_bytes >> 4, b_step = (2u * b_bytes) >> 4, wl_delta = b_bytes >> 4;
-        const bool fused = prm.fused != 0, no_mma = (prm.dbg & 16) != 0;
+        const bool fused = prm.fused != 0, no_mma = (prm.dbg & 16) != 0, fast = prm.fast != 0;
         const uint32_t acc_cols = (uint32_t)prm.acc_cols;
         Ring rs(HS), rb(BS), rc(NACC);
         if (p < NI)
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) conv_ss_kernel(const __grid_con
                                     uint32_t at = prm.taps == 9 ? a : a_base + (uint32_t)slot * a_step + (uint32_t)(p * kTW) * 8u;
                                     uint32_t acc = acc0 + (uint32_t)p * acc_cols;
                                     for (int t = p; t < gr.n; t += NI, at += (uint32_t)(NI * kTW) * 8u, acc += (uint32_t)NI * acc_cols)
-                                        issue_tile(fused, ksteps, acc, at, lo_delta, b, wl_delta, AH, BH, idw, idn, accum);
+                                        issue_tile(fused, ksteps, acc, at, lo_delta, b, wl_delta, AH, BH, idw, idn, accum, fast);
                                 }
                                 umma_commit(b_empty(bs));
                             }
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) conv_ss_kernel(const __grid_con
                             tc_fence_after();
                             if (elect_one()) {
                                 if (!no_mma)
-                                    issue_tile(fused, ksteps, acc0 + (uint32_t)t * acc_cols, a_base + (uint32_t)slot * a_step, lo_delta, b, wl_delta, AH, BH, idw, idn, accum);
+                                    issue_tile(fused, ksteps, acc0 + (uint32_t)t * acc_cols, a_base + (uint32_t)slot * a_step, lo_delta, b, wl_delta, AH, BH, idw, idn, accum, fast);
                                 umma_commit(src_empty(slot));
                             }
                             __syncwarp();
@@ -404,7 +408,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) conv_ss_kernel(const __grid_con
                 wait_p(src_full(slot), rs.phase, 7, prof);
                 const uint4 *src = reinterpret_cast<const uint4 *>(smem + (size_t)slot * prm.src_bytes);
                 uint4 *dst = reinterpret_cast<uint4 *>(smem + (size_t)(HS + slot) * prm.src_bytes);
-                for (int i = st; i < ((prm.dbg & 32) ? 0 : chunks); i += kSplitThreads) {
+                for (int i = st; i < (((prm.dbg & 32) || prm.fast) ? 0 : chunks); i += kSplitThreads) {
                     const uint4 x = src[i];
                     uint4 l;
                     l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(x.x & 0xFFFFE000u));
@@ -566,7 +570,8 @@ int ojdf_conv_ss_launch(const ojdf_conv_problem *problems_host, int n_problems, 
     prm.tiles_x = (W + ss::kTW - 1) / ss::kTW;
     prm.tiles_y = (H + ss::kTH - 1) / ss::kTH;
     prm.slope = slope; prm.out_mul = out_mul;
-    prm.fused = npad <= 64 ? 1 : 0;
+    prm.fast = (flags & 64) ? 1 : 0;                            // 1xTF32 (~1e-3 relative): BASELINE.json configs[2]'s fast mode
+    prm.fused = (npad <= 64 && !prm.fast) ? 1 : 0;
     prm.acc_cols = prm.fused ? 2 * npad : npad;
     // tensor memory: MT tiles x NACC accumulator sets x acc_cols columns <= 512.  Wide channel groups with a long K
     // loop trade the second accumulator set for twice the weight-stage reuse (their epilogue is a small share).

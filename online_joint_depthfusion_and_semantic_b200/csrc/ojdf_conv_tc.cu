@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     __shared__ __align__(8) uint64_t s_bars[2 * kMaxSrc + 2 * kMaxB + 2 * kAS + 4];
     __shared__ uint32_t s_tmem;
     __shared__ float2 s_ss[128];                                 // (scale, shift) of the epilogue's current channel group
+    __shared__ bool s_last;
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // warp-uniform role index
     const uint32_t raw = smem_u32(smem_raw);
@@ -390,6 +391,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                             for (int c = lane; c < nco; c += 32)
                                 orow[c] = *reinterpret_cast<const float *>(stg_ptr + (size_t)(c >> 5) * kSlabBytes + (size_t)rr * 128 +
                                                                            ((((c & 31) >> 2) ^ (rr & 7)) << 4) + ((c & 3) << 2));
+                        }
+                    }
+                }
+                if (prm.ksplit > 1 && prm.counters) {
+                    // this CTA's slice of the tile is written: count it; whoever delivers the last slice finishes the tile
+                    __threadfence();
+                    named_bar(1, kEpiThreads);
+                    const int tile_id = (gr.z * prm.groups + gr.g) * tiles + gr.col * prm.tiles_y + gr.row + mt;
+                    if (et == 0) {
+                        const unsigned int old = atomicAdd(&prm.counters[tile_id], 1u);
+                        s_last = old == (unsigned int)(prm.ksplit - 1);
+                        if (s_last) prm.counters[tile_id] = 0u;          // back to idle for the next launch
+                    }
+                    named_bar(1, kEpiThreads);
+                    if (s_last) {
+                        __threadfence();
+                        const SplitReduce &rd = prm.red[gr.z];
+                        int nco = prm.red_cout - co_base;
+                        if (nco > npad) nco = npad;
+                        const size_t slab = (size_t)prm.H * prm.W * prm.cpad;
+                        for (int i = et; i < 128 * nco; i += kEpiThreads) {
+                            const int rr = i / nco, c = i - rr * nco;
+                            const int px = gr.col * kBW + rr % kBW, py = (gr.row + mt) * kBH + rr / kBW;
+                            if (py >= prm.H || px >= prm.W) continue;
+                            const size_t pixi = (size_t)py * prm.W + px;
+                            const float *pp = rd.partial + pixi * prm.cpad + co_base + c;
+                            float a = 0.0f;
+                            for (int k = 0; k < prm.ksplit; ++k) a += __ldcg(pp + (size_t)k * slab);
+                            const int co = co_base + c;
+                            float v = fmaf(a, __ldg(rd.scale + co), __ldg(rd.shift + co));
+                            if (prm.red_act == kSigmoidMul) v = rd.residual[pixi * rd.res_stride + co] / (1.0f + expf(-v));
+                            else {
+                                if (rd.residual) v += rd.residual[pixi * rd.res_stride + co];
+                                v = activate(v, prm.red_act, prm.slope);
+                            }
+                            rd.out[pixi * rd.out_stride + rd.out_coff + co] = v * prm.red_out_mul;
                         }
                     }
                 }
@@ -718,12 +755,33 @@ extern "C" int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int 
         if (ks >= 2) prm.ksplit = ks;
     }
     tc::SplitReduce red[tc::kMaxBatch];
+    // flag 16384: finish the split-K layer inside this kernel (the CTA that delivers the last slice of a tile sums the
+    // slices; the first 16 KB of the scratch are then per-tile slice counters, zero before the first launch and left zero
+    // by every launch).  Measured on B200: one SM reducing a whole tile (1 MB of partials at 15x20 / 16 slices) takes
+    // longer than the separate, chip-wide conv_reduce_kernel launch it saves (85 vs 19 us per layer), so the default is
+    // the separate reduction.
+    const bool fused_reduce = (flags & 16384) != 0;
+    const size_t counter_floats = 4096;
+    if (prm.ksplit > 1 && fused_reduce) {
+        if (scratch_bytes < counter_floats * 4 + (size_t)2 * n_problems * H * W * prm.cpad * sizeof(float) || items > (long long)counter_floats) {
+            prm.ksplit = 1;
+        } else {
+            const size_t per_split = (size_t)n_problems * H * W * prm.cpad * sizeof(float);
+            const int fit = (int)((scratch_bytes - counter_floats * 4) / per_split);
+            if (prm.ksplit > fit) prm.ksplit = fit;
+            if (prm.ksplit < 2) prm.ksplit = 1;
+        }
+    }
     if (prm.ksplit > 1) {
+        float *part0 = scratch_dev + (fused_reduce ? counter_floats : 0);
+        prm.counters = fused_reduce ? reinterpret_cast<unsigned int *>(scratch_dev) : nullptr;
+        prm.red_act = act; prm.red_cout = cout; prm.red_out_mul = out_mul;
         for (int i = 0; i < n_problems; ++i) {
             const ojdf_conv_problem &q = problems_host[i];
-            float *part = scratch_dev + (size_t)i * prm.ksplit * H * W * prm.cpad;
+            float *part = part0 + (size_t)i * prm.ksplit * H * W * prm.cpad;
             red[i] = tc::SplitReduce{q.scale_dev, q.shift_dev, q.residual_dev, q.out_dev, part, q.out_stride, q.out_coffset,
                                      q.residual_stride};
+            prm.red[i] = red[i];
             prm.p[i].out = part;
             prm.p[i].residual = nullptr;
             prm.p[i].out_stride = prm.cpad;
@@ -751,7 +809,7 @@ extern "C" int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int 
         const cudaError_t le = cudaLaunchKernelEx(&cfg, tc::conv_tc_kernel, prm);
         if (le != cudaSuccess) { cudaGetLastError(); return (int)le; }
     }
-    if (prm.ksplit > 1) {
+    if (prm.ksplit > 1 && !prm.counters) {
         const int r = launched(1);
         if (r) return r;
         return launch_split_reduce(red, n_problems, H * W, cout, prm.cpad, prm.ksplit, act, slope, out_mul, (cudaStream_t)stream);

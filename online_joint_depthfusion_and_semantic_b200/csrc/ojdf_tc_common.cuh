@@ -42,6 +42,12 @@ struct Params {
     int tap_mask[kMaxBatch];            // live taps of each problem (bit t = tap t), never 0
     float *partial[kMaxBatch];          // split-K scratch per problem: [ksplit][H*W][cpad] raw partial sums
     float slope, out_mul;
+    // split-K finished inside the kernel: the CTA that delivers the LAST K slice of a tile sums the slices in slice order
+    // (deterministic) and applies the layer's real epilogue; `counters` (zero between launches) counts slices per tile
+    SplitReduce red[kMaxBatch];
+    unsigned int *counters;
+    int red_act, red_cout;
+    float red_out_mul;
 };
 
 // ---------------------------------------------------------------- PTX wrappers

@@ -15,6 +15,22 @@ class EngineOwner:
     _fp_tensors = None
     _fp_value = None
     _fp_hooked = False
+    precision = 'parity'        # 'parity': 3xTF32, ~1e-6 of fp32 (default); 'fast': 1xTF32, ~1e-3 (BASELINE.json configs[2])
+
+    def set_precision(self, mode):
+        """Arithmetic of the tensor-core convolutions of this module's launch plans.  'parity' (default) is the 3xTF32
+        split product (fp32-grade, meets the 1e-4 tolerance on logits / TSDF updates); 'fast' issues one TF32 MMA per MAC
+        (3x less tensor work, ~1e-3 relative) and is judged on label agreement / mIoU / F1 instead."""
+        if mode not in ('parity', 'fast'):
+            raise ValueError("precision must be 'parity' or 'fast'")
+        if mode != self.precision:
+            self.precision = mode
+            self._invalidate()
+        return self
+
+    @property
+    def conv_flags(self):
+        return 64 if self.precision == 'fast' else 0
 
     def _drop_engines(self):            # pragma: no cover - overridden
         raise NotImplementedError

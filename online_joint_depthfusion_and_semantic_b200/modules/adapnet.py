@@ -252,7 +252,7 @@ class AdapNet(EngineOwner, nn.Module):
         if e is None or (e.h, e.w) != (h, w) or e.device != pres[0].device:
             encs = [self.encoder_mod1] + ([self.encoder_mod2] if self.stage != 1 else [])
             heads = [self.eASPP] if self.stage == 1 else [self.eASPP_mod1, self.eASPP_mod2]
-            e = self._engine = EncoderTailEngine(encs, heads, h, w, pres[0].device)
+            e = self._engine = EncoderTailEngine(encs, heads, h, w, pres[0].device, flags=self.conv_flags)
         return e.forward(pres)
 
     def set_bottleneck_dropout(self, enabled):

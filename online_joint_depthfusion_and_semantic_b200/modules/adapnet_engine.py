@@ -123,10 +123,12 @@ class EncoderTailEngine:
     SCRATCH_BYTES = 96 << 20
     PARTIAL_BLOCKS = 296
 
-    def __init__(self, encoders, aspps, h, w, device, out_buf=None):
+    def __init__(self, encoders, aspps, h, w, device, out_buf=None, flags=0):
         """encoders: [Encoder, ...] (1 or 2), aspps: matching eASPP modules; h, w: tail resolution.
         out_buf: optional (h*w, n*256) buffer the eASPP outputs are written into side by side."""
         self.h, self.w, self.N, self.device = int(h), int(w), int(h) * int(w), torch.device(device)
+        self.flags = int(flags)
+        self.side = None
         dev, N, n = self.device, self.N, len(encoders)
         self.n = n
         units = [[_Unit(m, dev) for m in list(e.res_n50_enc.layer3)[1:] + list(e.res_n50_enc.layer4)] for e in encoders]
@@ -137,7 +139,7 @@ class EncoderTailEngine:
         self.cin0 = units[0][0].cin
         self.X = [[z(cmax), z(cmax)] for _ in range(n)]                       # ping-pong unit input / output
         T1, T2, D = [z(512) for _ in range(n)], [z(512) for _ in range(n)], [z(cmax) for _ in range(n)]
-        self.scratch = torch.empty(self.SCRATCH_BYTES // 4, dtype=torch.float32, device=dev)
+        self.scratch = torch.zeros(self.SCRATCH_BYTES // 4, dtype=torch.float32, device=dev)   # zero: the first 16 KB are the split-K slice counters
         self.partial = torch.empty(self.PARTIAL_BLOCKS * 2048, dtype=torch.float32, device=dev)
         self._keep += [T1, T2, D]
         self.plan = []
@@ -176,6 +178,9 @@ class EncoderTailEngine:
         self.out = [z(co) for _ in range(n)] if out_buf is None else None
         self._keep += [cat, U]
         ms = _pad4(mid)
+        # eASPP's pooled branch -> bias of the final conv: thin reductions only the LAST conv of the head needs; they run on a
+        # side stream next to the branch convolutions (also inside a captured CUDA graph: a fork / join of the capture)
+        self.plan.append(('fork_bias',))
         for e in range(n):
             self.plan.append(('bias', heads[e], feat[e], cmax))
         conv_step([(heads[e].b1, heads[e].b1.problem(feat[e], cmax, cat[e], 4 * co, 0)) for e in range(n)])
@@ -184,6 +189,7 @@ class EncoderTailEngine:
         conv_step([(heads[e].br[b][2], heads[e].br[b][2].problem(U[e][b][1], ms, U[e][b][0], ms)) for e in range(n) for b in range(3)])
         conv_step([(heads[e].br[b][3], heads[e].br[b][3].problem(U[e][b][0], ms, cat[e], 4 * co, (b + 1) * co))
                    for e in range(n) for b in range(3)])
+        self.plan.append(('join_bias',))
         if out_buf is None:
             conv_step([(heads[e].fin, heads[e].fin.problem(cat[e], 4 * co, self.out[e], co, 0, shift=heads[e].frame_shift))
                        for e in range(n)])
@@ -193,15 +199,20 @@ class EncoderTailEngine:
         self.cmax, self.cout = cmax, co
 
     def run(self, st):
-        """Walk the plan on stream `st`; X[e][0] must hold the (N, 1024) pixel-major input of encoder e."""
+        """Walk the plan on the current stream (`st` = its handle); X[e][0] must hold the (N, 1024) pixel-major input of
+        encoder e."""
         L = _lib.lib()
         N, H, W = self.N, self.h, self.w
+        main = torch.cuda.current_stream(self.device)
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=self.device)
+        side = self.side
         for step in self.plan:
             kind = step[0]
             if kind == 'conv':
                 _, arr, n, cin, cout, taps, act, slope, npad_req = step
                 if self.tc:
-                    _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 0,
+                    _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, self.flags,
                                                       self.scratch.data_ptr(), self.scratch.numel() * 4, st))
                 else:
                     _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0,
@@ -209,12 +220,16 @@ class EncoderTailEngine:
             elif kind == 'dropout':
                 for t in step[1]:                            # reference quirk: active in eval mode
                     t.copy_(F.dropout(t, p=0.5, training=True))
+            elif kind == 'fork_bias':
+                side.wait_stream(main)
+            elif kind == 'join_bias':
+                main.wait_stream(side)
             else:
                 _, a, src, ss = step
                 _lib.check(L.ojdf_gap_bias(src.data_ptr(), ss, N, a.cin, a.wg.data_ptr(), a.g_scale.data_ptr(),
                                            a.g_shift.data_ptr(), a.cout, 1, a.wf5.data_ptr(), a.fin.scale.data_ptr(),
                                            a.fin.shift.data_ptr(), a.cout, self.partial.data_ptr(), self.PARTIAL_BLOCKS,
-                                           a.frame_shift.data_ptr(), st))
+                                           a.frame_shift.data_ptr(), side.cuda_stream))
 
     def forward(self, xs):
         """xs: list of (1, C, h, w) NCHW tensors (output of layer3[0] of each encoder).
@@ -333,7 +348,8 @@ class AdapNetEngine:
         self.seg_ids = torch.empty(1, h, w, dtype=torch.uint8, device=dev)
         self.seg_frame = torch.empty(1, h, w, dtype=torch.float32, device=dev)
         self.FX = z(N16, n * 256)                              # eASPP outputs of all encoders side by side
-        self.tail = EncoderTailEngine(encs, aspps, H16, W16, dev, out_buf=self.FX)
+        self.flags = int(getattr(net, 'conv_flags', 0))
+        self.tail = EncoderTailEngine(encs, aspps, H16, W16, dev, out_buf=self.FX, flags=self.flags)
         cur, cs = self.S0, 64
         for ui in range(len(encs[0].res_n50_enc.layer1)):
             ms = [e.res_n50_enc.layer1[ui] for e in encs]
@@ -444,7 +460,7 @@ class AdapNetEngine:
                 kind = step[0]
                 if kind == 'conv':
                     _, arr, n, cin, cout, H, W, taps, act, slope, npad_req = step
-                    _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 1,
+                    _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 1 | self.flags,
                                                       self.tail.scratch.data_ptr(), self.tail.scratch.numel() * 4, st))
                 elif kind == 'tail':
                     self.tail.run(st)

@@ -201,6 +201,8 @@ class FusionNetEngine:
         self.partial = torch.empty(self.PARTIAL_BLOCKS * 256, dtype=torch.float32, device=dev)
         self.plan = []
         self.tc = conv_mode() == 'tc'
+        self.side = None
+        self.flags = 1 | int(getattr(net, 'conv_flags', 0))        # 1: the pad channels are ours; 64: 1xTF32 (precision 'fast')
 
         def conv_step(convs_problems):
             """convs_problems: list of (conv, problem) with identical shapes -> one batched launch."""
@@ -227,6 +229,9 @@ class FusionNetEngine:
             P2 = [z(mid_s) for _ in range(n)]                                       # pool(pool(Y_3))
             br_out = [z(4 * Cvp) for _ in range(n)]
             self._keep += [tb, Y, P1, P2, br_out]
+            # global-pool branch -> bias of the final conv: a long, thin reduction (two launches, one of them a single
+            # block) that only the LAST conv of the vortex needs: it runs on a side stream next to the branch convolutions
+            self.plan.append(('fork_bias',))
             for i, v in enumerate(vs):
                 self.plan.append(('bias', v, srcs[i], src_stride))
             # branch 0: 1x1 + BN + ReLU on x; branches 1..3: the bare 1x1 product on x, then the cascaded pools
@@ -250,6 +255,7 @@ class FusionNetEngine:
                        for i in range(n) for b in range(4)])
             conv_step([(vs[i].branches[b][3], vs[i].branches[b][3].problem(tb[i][b][0], mid_s, br_out[i], 4 * Cvp, b * Cvp))
                        for i in range(n) for b in range(4)])
+            self.plan.append(('join_bias',))                     # the final conv reads the frame shifts computed on the side stream
             conv_step([(vs[i].final, vs[i].final.problem(br_out[i], 4 * Cvp, dsts[i][0], dsts[i][1], dsts[i][2],
                                                          shift=vs[i].frame_shift)) for i in range(n)])
 
@@ -299,7 +305,11 @@ class FusionNetEngine:
             assert sem_frame is not None
             sem_frame = sem_frame.detach().float().contiguous()
         with torch.cuda.device(dev), _lib.timed('fusionnet', dev):
-            st = _lib.stream_ptr(dev)
+            main = torch.cuda.current_stream(dev)
+            st = main.cuda_stream
+            if self.side is None:
+                self.side = torch.cuda.Stream(device=dev)
+            side = self.side
             if not packed:                                       # packed: the extractor's gather already wrote the input rows
                 _lib.check(L.ojdf_pack_fusion_input(vals.data_ptr(), wts.data_ptr(), frame.data_ptr(),
                                                     sem_frame.data_ptr() if self.two else None, N, P, self.in_bufs[0].data_ptr(),
@@ -310,7 +320,7 @@ class FusionNetEngine:
                     _, arr, n, cin, cout, taps, act, slope = step[:8]
                     out_mul = step[8] if len(step) > 8 else 1.0
                     if self.tc:
-                        _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, 0, 1, None, 0, st))   # 1: pads are ours
+                        _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, 0, self.flags, None, 0, st))
                     else:
                         _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, None, 0, st))
                 elif kind == 'pools':
@@ -319,10 +329,14 @@ class FusionNetEngine:
                 elif kind == 'pool':
                     _, src, ss, ch, dst, ds = step
                     _lib.check(L.ojdf_avgpool3_nhwc(src.data_ptr(), ss, H, W, ch, dst.data_ptr(), ds, st))
+                elif kind == 'fork_bias':
+                    side.wait_stream(main)                       # the vortex input is complete on the main stream
+                elif kind == 'join_bias':
+                    main.wait_stream(side)
                 else:
                     _, v, src, ss = step
                     _lib.check(L.ojdf_vortex_bias(src.data_ptr(), ss, N, v.cin, v.wg.data_ptr(), v.g_scale.data_ptr(),
                                                   v.g_shift.data_ptr(), v.cout, v.wf1.data_ptr(), v.final.scale.data_ptr(),
                                                   v.final.shift.data_ptr(), v.cout, self.partial.data_ptr(),
-                                                  self.PARTIAL_BLOCKS, v.frame_shift.data_ptr(), st))
+                                                  self.PARTIAL_BLOCKS, v.frame_shift.data_ptr(), side.cuda_stream))
         return self.est

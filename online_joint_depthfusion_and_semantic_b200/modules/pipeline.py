@@ -54,6 +54,14 @@ class Pipeline(nn.Module):
         self._seg_graph_fn = None
         self._sem_frame = None
 
+    def set_precision(self, mode):
+        """'parity' (3xTF32, default) or 'fast' (1xTF32) for the tensor-core convolutions of both networks."""
+        self._seg_graph = None
+        self._fusion_network.set_precision(mode)
+        if self._semantic_2d_network is not None:
+            self._semantic_2d_network.set_precision(mode)
+        return self
+
     def train(self, mode=True):
         self._seg_graph = None               # captured graphs hold parameter addresses / modes
         return super().train(mode)

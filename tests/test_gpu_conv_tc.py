@@ -37,6 +37,9 @@ CASES = [
     ('1x1 one M-tile per group (flag 2)', 48, 64, 95, 19, 1, 1, 116, 116, 95, 2, False, 2, 0, 2),
     ('3x3 15x20 512 -> 256 mixed dilations, residual, split K', 15, 20, 512, 256, 9, 4, 512, 256, 0, 1, True, 4, 0, 0),
     ('3x3 15x20 512 -> 512 without the K split (flag 4096)', 15, 20, 512, 512, 9, 1, 512, 512, 0, 1, False, 1, 0, 4096),
+    ('3x3 15x20 512 -> 256 split K finished inside the kernel (flag 16384)', 15, 20, 512, 256, 9, 4, 512, 256, 0, 1, True, 4, 0, 16384),
+    ('1x1 15x20 1024 -> 256 split K inside the kernel, sigmoid gate (act 5)', 15, 20, 1024, 256, 1, 1, 1024, 256, 0, 5, True, 2, 0, 16384),
+    ('3x3 30x40 48 -> 48 sigmoid gate (act 5) on the shared-memory-operand kernel', 30, 40, 48, 48, 9, 1, 48, 48, 0, 5, True, 1, 0, 0),
 ]
 
 
@@ -58,9 +61,12 @@ def _run(case):
         xin = x[:, :cin].double().t().reshape(1, cin, H, W)
         y = torch.nn.functional.conv2d(xin, w.double(), padding=d * (k // 2), dilation=d)[0].reshape(cout, H * W).t()
         y = y * sc.double() + sh.double()
-        if use_res:
-            y = y + res.double()
-        y = {0: y, 1: y.clamp(min=0), 2: torch.where(y > 0, y, 0.01 * y), 3: torch.tanh(y), 4: torch.sigmoid(y)}[act]
+        if act == 5:                                                        # SSMA gate: sigmoid(conv) * gated tensor
+            y = torch.sigmoid(y) * res.double()
+        else:
+            if use_res:
+                y = y + res.double()
+            y = {0: y, 1: y.clamp(min=0), 2: torch.where(y > 0, y, 0.01 * y), 3: torch.tanh(y), 4: torch.sigmoid(y)}[act]
         out = torch.full((H * W, ostr), 7.0, device=DEV)
         t = [x.to(DEV), torch.from_numpy(packed).to(DEV), sc.to(DEV), sh.to(DEV), out, res.to(DEV) if use_res else None]
         keep.append(t)
@@ -69,7 +75,7 @@ def _run(case):
         refs.append(y)
         outs.append(out)
     arr = (ConvProblem * nprob)(*probs)
-    scratch = torch.empty((32 << 20) // 4, dtype=torch.float32, device=DEV)     # lets small maps split their K loop
+    scratch = torch.zeros((32 << 20) // 4, dtype=torch.float32, device=DEV)     # lets small maps split their K loop (zero: slice counters)
     _lib.check(L.ojdf_conv_tc_batched(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, npad_req, flags, scratch.data_ptr() if scratch is not None else None,
                                       scratch.numel() * 4 if scratch is not None else 0, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()

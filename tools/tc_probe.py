@@ -112,7 +112,7 @@ def run_case(idx, timing):
         outs.append(out)
     arr = (ConvProblem * nprob)(*probs)
     st = torch.cuda.current_stream().cuda_stream
-    scratch = torch.empty((64 << 20) // 4, dtype=torch.float32, device=dev)
+    scratch = torch.zeros((64 << 20) // 4, dtype=torch.float32, device=dev)
     scratch_ptr, scratch_bytes = scratch.data_ptr(), scratch.numel() * 4
     _lib.check(getattr(L, FN)(arr, nprob, cin, cout, H, W, taps, act, 0.01, 1.0, (flags >> 16) & 255, flags & 0x1ffff, scratch_ptr, scratch_bytes, st))
     torch.cuda.synchronize()
