@@ -148,21 +148,15 @@ int ojdf_integrate_updates(const float *values_dev, const int64_t *idx_dev, cons
                            uint8_t *ids_vol_dev, void *scores_vol_dev, int do_semantics,
                            void *workspace_dev, size_t workspace_bytes, void *stream);
 
-/* ---- a10: FusionNet layers (modules/model.py:4-283), pixel-major (NHWC) fp32 activations ------
- * One "tap GEMM" covers every convolution of FusionNet_v2/v3:
- *   out[p, coff+co] = out_mul * act(scale[co] * sum_tap sum_ci in[p + tap*dilation, ci] * W[tap,ci,co] + shift[co])
- * taps = 1 (1x1) or 9 (3x3, zero padding = dilation); act: 0 none, 1 ReLU, 2 LeakyReLU(slope), 3 tanh.
- * scale/shift carry the conv bias and the inference BatchNorm (Block / Pred / VortexPooling layers).
- * in: (H*W, in_stride) floats, in_stride % 4 == 0, channels [0,cin) are read;
- * weights: [ceil(cout/20)][taps][8*ceil(cin/8)][20] floats, zero padded (the host mirror builds it from
- * the module's Conv2d weight); out: (H*W, out_stride) floats. */
-int ojdf_conv_nhwc(const float *in_dev, int in_stride, int cin, int H, int W, int taps, int dilation,
-                   const float *weights_dev, const float *scale_dev, const float *shift_dev, int cout,
-                   int act, float slope, float out_mul, float *out_dev, int out_stride, int out_coffset,
-                   void *stream);
-/* Up to 8 independent convolutions of identical shape (cin, cout, taps, H, W, activation) in ONE
- * launch -- the two FusionNet heads, the four VortexPooling branches (each with its own dilation).
- * `problems_host` is a host array read during the call. */
+/* ---- a10 / a17: FusionNet and AdapNet++ layers (modules/model.py:4-283, modules/adapnet.py:12-415), pixel-major (NHWC)
+ * fp32 activations.  One "tap GEMM" covers every convolution of both networks:
+ *   out[p, coff+co] = out_mul * act(scale[co] * sum_tap sum_ci in[p + tap*dilation, ci] * W[tap,ci,co] + shift[co] (+ residual))
+ * taps = 1 (1x1) or 9 (3x3, zero padding = dilation); act: 0 none, 1 ReLU, 2 LeakyReLU(slope), 3 tanh, 4 sigmoid,
+ * 5 = sigmoid(v) * residual (the SSMA gate, modules/adapnet.py:352; residual_dev required).
+ * scale/shift carry the conv bias and the inference BatchNorm.  in: (H*W, in_stride) floats, in_stride % 4 == 0, channels
+ * [0,cin) are read; out: (H*W, out_stride) floats.  Up to 8 independent convolutions of identical shape (cin, cout, taps,
+ * H, W, activation) go in ONE launch -- the two FusionNet heads, the four VortexPooling branches (each with its own
+ * dilation), the two AdapNet++ encoders.  `problems_host` is a host array read during the call. */
 typedef struct ojdf_conv_problem {
     const float *in_dev;
     const float *weights_dev;
@@ -181,14 +175,7 @@ typedef struct ojdf_conv_problem {
     int tap_mask;                   /* 3x3 only: bit t set = tap t (ky*3+kx) contributes; 0 = all nine.  Taps whose shifted
                                      * window lies entirely outside the image are dropped automatically */
 } ojdf_conv_problem;
-/* act additionally accepts 4 = sigmoid and (tensor-core kernels) 5 = sigmoid(v) * residual (the SSMA gate,
- * modules/adapnet.py:352; residual_dev required).  scratch_dev (optional, scratch_bytes): when the pixel count
- * alone cannot fill the GPU (AdapNet++'s 15x20 maps) the K loop is split across blocks, partial sums go
- * to the scratch and a second kernel reduces them in a fixed order (deterministic). */
-int ojdf_conv_nhwc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
-                           int taps, int act, float slope, float out_mul, float *scratch_dev, size_t scratch_bytes,
-                           void *stream);
-/* ---- a10/a17 on the tensor cores (csrc/ojdf_conv_tc.cu): the same tap GEMM as ojdf_conv_nhwc_batched,
+/* ---- the tap GEMM on the tensor cores (csrc/ojdf_conv_tc.cu, csrc/ojdf_conv_ss.cu),
  * computed by tcgen05.mma (kind::tf32, fp32 TMEM accumulators) with a 3xTF32 split-precision product
  * (x = hi + lo; hi*hi + lo*hi + hi*lo), i.e. fp32-grade results (~1e-6 relative).  Replaces the
  * reference's per-layer cuDNN convolution + BatchNorm + activation launches of modules/model.py:4-283 and

@@ -32,8 +32,6 @@ _SIGNATURES = {
     'ojdf_integrate_apply': (_i, [_vp, _i64, _i, _i, _f, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     'ojdf_integrate_updates': (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i,
                                     _vp, _sz, _vp]),
-    'ojdf_conv_nhwc': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _i, _i, _vp]),
-    'ojdf_conv_nhwc_batched': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _sz, _vp]),
     'ojdf_conv_tc_layout': (_i, [_i, _i, _vp, _vp]),
     'ojdf_conv_tc_weight_floats': (_sz, [_i, _i, _i, _i]),
     'ojdf_conv_tc_pack_weights': (_i, [_vp, _i, _i, _i, _i, _vp]),

@@ -1,38 +1,20 @@
-// FusionNet convolution stack (modules/model.py:4-283 of the reference) as fp32-exact sm_100a
-// kernels on pixel-major (NHWC) activations.
-//
-// Every FusionNet layer is a small-channel "tap GEMM": out[p, co] = act(scale[co] * sum_tap sum_ci
-// in[p + tap*dil, ci] * W[tap, ci, co] + shift[co]) with taps = 1 (1x1) or 9 (3x3, any dilation),
-// Cin in {19..570} and Cout in {9, 19, .., 114}.  The reference issues one cuDNN convolution, one
-// batch-norm and one activation kernel per layer and materialises every torch.cat; here
-//   * BatchNorm (inference statistics), bias and the activation are the epilogue of the conv kernel,
-//   * dense-block / vortex concatenations are channel offsets into one pixel-major buffer,
-//   * the global-average-pool branch of VortexPooling collapses into a per-frame bias vector.
-// The arithmetic stays fp32 FMA (parity within 1e-5 of the reference's fp32 convolutions); the
-// tensor-core (tcgen05, bf16 / 3xTF32) version of the same tap-GEMM is the next step.
-//
-// conv kernel (v4): one thread owns 4 pixels x 20 output channels in registers (80 FMAs per 6 LDS.128),
-// one warp owns 128 consecutive pixels and runs its own barrier-free cp.async pipeline.
-// A block covers a pixel tile of one convolution; up to 8 independent, equally shaped convolutions
-// (the two FusionNet heads, the four VortexPooling branches) are batched along blockIdx.z and the
-// host sizes tiles / block width (96..160 threads) so that the grid is a whole number of waves over
-// the 148 SMs with several blocks co-resident per SM.  Inputs AND weights are streamed through
-// shared memory in 8-channel chunks by a 3-stage cp.async pipeline (coalesced 16-byte copies, zero
-// fill for the convolution padding): global memory is read once per tap with full-sector efficiency,
-// weights arrive as [8 ci][20 co] slices read back as broadcast LDS.128.
+// Small kernels around the tensor-core convolutions of FusionNet / AdapNet++ (modules/model.py:4-283,
+// modules/adapnet.py:152-216), pixel-major (NHWC) fp32 activations:
+//   * conv_reduce_kernel     : second half of a split-K convolution (fixed summation order, the layer's epilogue);
+//   * avgpool3 kernels       : VortexPooling's cascaded 3x3 average pools (modules/model.py:114-116), batched, with an
+//                              optional scale/shift/ReLU epilogue (the pools commute with the branch's first 1x1 conv);
+//   * channel_sum / gap_bias : the global-average-pool branches of VortexPooling and eASPP collapse into a per-frame bias
+//                              vector of the block's final 1x1 convolution;
+//   * pack_input             : FusionNet's input rows [values | weights | depth or label] (modules/pipeline.py:74-102);
+//   * NCHW <-> NHWC transposes for the tail-only AdapNet++ engine.
+// The convolutions themselves live in ojdf_conv_tc.cu (A operand in tensor memory) and ojdf_conv_ss.cu (both operands
+// in shared memory).
 #include <numeric>
 
 #include "ojdf_internal.h"
 
 namespace ojdf {
 
-constexpr int kGroup = 20;          // output channels per thread (19 padded to 20 for FusionNet)
-constexpr int kPix = 2;             // pixels per thread
-constexpr int kMaxCT = 160;         // widest block (5 warps)
-constexpr int kKC = 8;              // channels per pipeline chunk
-constexpr int kRow4 = kKC / 4 + 1;  // float4 per staged pixel row (+1 pad: odd stride, conflict-free LDS.128)
-constexpr int kWChunk4 = kKC * kGroup / 4;           // float4 of weights per chunk (8 ci x 20 co)
-constexpr int kStages = 3;
 constexpr int kMaxBatch = 8;
 
 enum Act { kNone = 0, kRelu = 1, kLeaky = 2, kTanh = 3, kSigmoid = 4, kSigmoidMul = 5 };
@@ -52,169 +34,6 @@ __device__ __forceinline__ float activate(float v, int act, float slope)
     if (act == kTanh) return tanhf(v);
     if (act == kSigmoid) return 1.0f / (1.0f + expf(-v));
     return v;
-}
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    const int bytes = valid ? 16 : 0;                  // 0 -> the 16 bytes are zero filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// weights: [groups][taps][cin8][kGroup] fp32, zero padded (cin8 = cin rounded up to 8).
-// dynamic smem: per warp, kStages x { 128 pixel rows of kRow4 float4, then kWChunk4 float4 of weights }.
-// Every warp runs its own cp.async pipeline over its own 128 pixels (lane l owns pixels l, l+32, l+64,
-// l+96 of the warp's slice), so the main loop has no block-wide barrier at all.
-constexpr int kWarpPix = 32 * kPix;                            // 128
-constexpr int kWarpStage4 = kWarpPix * kRow4 + kWChunk4;       // float4 per warp per stage
-
-template <int TAPS>
-__global__ void __launch_bounds__(kMaxCT, 3)
-conv_tile_kernel(ConvBatch batch, int cin, int H, int W, int tile_px, int cout, int act, float slope, float out_mul,
-                 int splits)
-{
-    extern __shared__ float4 smem4[];
-    const int split = blockIdx.z % splits;
-    const ConvProblem pr = batch.p[blockIdx.z / splits];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cin8 = (cin + kKC - 1) / kKC * kKC, nk = cin8 / kKC, cin4 = (cin + 3) >> 2;
-    const int g = blockIdx.y;
-    const float4 *wg = reinterpret_cast<const float4 *>(pr.weights) + (size_t)g * (TAPS * cin8 * (kGroup / 4));
-    float4 *wsm = smem4 + (size_t)warp * (kStages * kWarpStage4);
-
-    const int npix = H * W;
-    const int tile0 = blockIdx.x * tile_px + warp * kWarpPix;
-    const int tile_end = min(blockIdx.x * tile_px + tile_px, npix);
-    // staging role: this lane copies float4 column (lane & 1) of the warp's pixels lane/2 + 16*i, i < 8.
-    // Per staged pixel: element offset of the pixel row and a 9-bit mask of the taps that stay inside
-    // the image (zero padding elsewhere).
-    const int sc4 = lane & 1;
-    int s_off[2 * kPix];
-    unsigned s_ok[2 * kPix];
-#pragma unroll
-    for (int i = 0; i < 2 * kPix; ++i) {
-        const int p = tile0 + (lane >> 1) + 16 * i;
-        const int y = p / W, x = p - y * W;
-        s_off[i] = p * pr.in_stride;
-        unsigned m = 0;
-        if (p < tile_end) {
-#pragma unroll
-            for (int tap = 0; tap < TAPS; ++tap) {
-                const int yy = y + (TAPS == 1 ? 0 : (tap / 3 - 1) * pr.dil), xx = x + (TAPS == 1 ? 0 : (tap % 3 - 1) * pr.dil);
-                if (yy >= 0 && yy < H && xx >= 0 && xx < W) m |= 1u << tap;
-            }
-        }
-        s_ok[i] = m;
-    }
-    const int nchunks_all = TAPS * nk;
-    const int ch_begin = (int)((long long)nchunks_all * split / splits);       // this block's slice of the K loop
-    const int nchunks = (int)((long long)nchunks_all * (split + 1) / splits) - ch_begin;
-    int i_tap = ch_begin / nk, i_k8 = ch_begin - (ch_begin / nk) * nk;            // (tap, k8) of the next chunk to issue
-    auto issue = [&](int ch) {
-        if (ch < nchunks) {
-            const int dy = TAPS == 1 ? 0 : (i_tap / 3 - 1) * pr.dil, dx = TAPS == 1 ? 0 : (i_tap % 3 - 1) * pr.dil;
-            const int c4 = i_k8 * (kKC / 4) + sc4;
-            const int shift = (dy * W + dx) * pr.in_stride + c4 * 4;
-            const bool col_ok = c4 < cin4;
-            float4 *dst = wsm + (size_t)(ch % kStages) * kWarpStage4;
-#pragma unroll
-            for (int i = 0; i < 2 * kPix; ++i) {
-                const bool ok = col_ok && ((s_ok[i] >> i_tap) & 1u);
-                cp_async16(dst + ((lane >> 1) + 16 * i) * kRow4 + sc4, pr.in + (ok ? s_off[i] + shift : 0), ok);
-            }
-            const float4 *wsrc = wg + (size_t)(i_tap * cin8 + i_k8 * kKC) * (kGroup / 4);
-            cp_async16(dst + kWarpPix * kRow4 + lane, wsrc + lane, true);
-            if (lane < kWChunk4 - 32) cp_async16(dst + kWarpPix * kRow4 + 32 + lane, wsrc + 32 + lane, true);
-            if (++i_k8 == nk) { i_k8 = 0; ++i_tap; }
-        }
-        cp_async_commit();
-    };
-    issue(0);
-    issue(1);
-
-    float acc[kPix][kGroup];
-#pragma unroll
-    for (int j = 0; j < kPix; ++j)
-#pragma unroll
-        for (int c = 0; c < kGroup; ++c) acc[j][c] = 0.0f;
-    const int tail = cin & 3;                          // real channels in the last float4 (0 = all four)
-
-    int k8 = ch_begin % nk;
-    for (int ch = 0; ch < nchunks; ++ch) {
-        cp_async_wait<1>();                            // this lane's copies of chunk ch have landed
-        __syncwarp();                                  // ... and every lane's; stage (ch+2)%3 is free again
-        issue(ch + 2);
-        const float4 *xs = wsm + (size_t)(ch % kStages) * kWarpStage4;
-        const float4 *wt = xs + kWarpPix * kRow4;
-#pragma unroll
-        for (int h4 = 0; h4 < kKC / 4; ++h4) {
-            float4 xv[kPix];
-#pragma unroll
-            for (int j = 0; j < kPix; ++j) xv[j] = xs[(lane + 32 * j) * kRow4 + h4];
-            if (tail && k8 * (kKC / 4) + h4 == cin4 - 1) {     // never let a neighbouring tensor's channels in
-#pragma unroll
-                for (int j = 0; j < kPix; ++j) {
-                    if (tail < 2) xv[j].y = 0.f;
-                    if (tail < 3) xv[j].z = 0.f;
-                    xv[j].w = 0.f;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                for (int q = 0; q < kGroup / 4; ++q) {
-                    const float4 wv = wt[(h4 * 4 + k) * (kGroup / 4) + q];
-#pragma unroll
-                    for (int j = 0; j < kPix; ++j) {
-                        const float x = k == 0 ? xv[j].x : (k == 1 ? xv[j].y : (k == 2 ? xv[j].z : xv[j].w));
-                        acc[j][4 * q + 0] = fmaf(x, wv.x, acc[j][4 * q + 0]);
-                        acc[j][4 * q + 1] = fmaf(x, wv.y, acc[j][4 * q + 1]);
-                        acc[j][4 * q + 2] = fmaf(x, wv.z, acc[j][4 * q + 2]);
-                        acc[j][4 * q + 3] = fmaf(x, wv.w, acc[j][4 * q + 3]);
-                    }
-                }
-            }
-        }
-        if (++k8 == nk) k8 = 0;
-    }
-    cp_async_wait<0>();
-    const int co0 = g * kGroup;
-    if (splits > 1) {                                  // raw partial sums; conv_reduce_kernel finishes the layer
-        const int cpad = gridDim.y * kGroup;
-#pragma unroll
-        for (int j = 0; j < kPix; ++j) {
-            const int p = tile0 + lane + 32 * j;
-            if (p >= tile_end) continue;
-            float4 *o = reinterpret_cast<float4 *>(pr.partial + ((size_t)split * npix + p) * cpad + co0);
-#pragma unroll
-            for (int q = 0; q < kGroup / 4; ++q) o[q] = make_float4(acc[j][4 * q], acc[j][4 * q + 1], acc[j][4 * q + 2], acc[j][4 * q + 3]);
-        }
-        return;
-    }
-    float sc[kGroup], sh[kGroup];
-#pragma unroll
-    for (int c = 0; c < kGroup; ++c) {
-        const bool live = co0 + c < cout;
-        sc[c] = live ? __ldg(pr.scale + co0 + c) : 0.f;
-        sh[c] = live ? __ldg(pr.shift + co0 + c) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < kPix; ++j) {
-        const int p = tile0 + lane + 32 * j;
-        if (p >= tile_end) continue;
-        float *o = pr.out + (size_t)p * pr.out_stride + pr.out_coff + co0;
-        const float *r = pr.residual ? pr.residual + (size_t)p * pr.res_stride + co0 : nullptr;
-#pragma unroll
-        for (int c = 0; c < kGroup; ++c)
-            if (co0 + c < cout) {
-                float v = fmaf(acc[j][c], sc[c], sh[c]);
-                if (r) v += r[c];
-                o[c] = activate(v, act, slope) * out_mul;
-            }
-    }
 }
 
 // Second half of a split-K convolution: sum the partials in split order, then the same epilogue.
@@ -505,98 +324,6 @@ int launch_split_reduce(const SplitReduce *problems, int n, int npix, int cout, 
 }  // namespace ojdf
 
 using namespace ojdf;
-
-// Pick the tile count and block width: whole waves over the SMs, lanes as full as possible.
-static void conv_geometry(int npix, int blocks_per_tile, int &tiles, int &tile_px, int &threads)
-{
-    const int sms = 148;
-    double best = 1e30;
-    const int tmin = (npix + kMaxCT * kPix - 1) / (kMaxCT * kPix);
-    for (int t = tmin; t <= tmin * 4 + sms; ++t) {
-        const int px = (npix + t - 1) / t;
-        const int th = ((px + kPix - 1) / kPix + 31) / 32 * 32;
-        if (th > kMaxCT) continue;
-        const int real_tiles = (npix + px - 1) / px;
-        const long long blocks = (long long)real_tiles * blocks_per_tile;
-        const double cost = (double)((blocks + sms - 1) / sms) * th;   // rounds x time per round
-        if (cost < best - 1e-9) { best = cost; tiles = real_tiles; tile_px = px; threads = th; }
-    }
-}
-
-static int launch_conv(ConvBatch &batch, int n, int cin, int cout, int H, int W, int taps, int act, float slope,
-                       float out_mul, float *scratch, size_t scratch_bytes, cudaStream_t s)
-{
-    const int npix = H * W;
-    const int groups = (cout + kGroup - 1) / kGroup, cpad = groups * kGroup;
-    const int nchunks = taps * ((cin + kKC - 1) / kKC);
-    // split the K loop when the pixels alone cannot fill the machine (AdapNet's 15x20 feature maps)
-    const long long warps = (long long)((npix + 32 * kPix - 1) / (32 * kPix)) * groups * n;
-    int splits = 1;
-    if (scratch && warps < 148 * 8) {
-        splits = (int)((148 * 16 + warps - 1) / warps);
-        if (splits > nchunks / 4) splits = nchunks / 4;          // keep >= 4 chunks per slice
-        if (splits > 32) splits = 32;
-        const size_t per_split = (size_t)n * npix * cpad * sizeof(float);
-        if (per_split && (size_t)splits * per_split > scratch_bytes) splits = (int)(scratch_bytes / per_split);
-        if (splits < 2) splits = 1;
-    }
-    if (splits > 1)
-        for (int i = 0; i < n; ++i) batch.p[i].partial = scratch + (size_t)i * splits * npix * cpad;
-    int tiles = 1, tile_px = npix, threads = 32;
-    conv_geometry(npix, groups * n * splits, tiles, tile_px, threads);
-    const size_t smem = (size_t)(threads / 32) * kStages * kWarpStage4 * sizeof(float4);
-    dim3 grid(tiles, groups, n * splits);
-    if (taps == 1) {
-        static bool attr1 = false;
-        if (!attr1) { cudaFuncSetAttribute(conv_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr1 = true; }
-        conv_tile_kernel<1><<<grid, threads, smem, s>>>(batch, cin, H, W, tile_px, cout, act, slope, out_mul, splits);
-    } else {
-        static bool attr9 = false;
-        if (!attr9) { cudaFuncSetAttribute(conv_tile_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr9 = true; }
-        conv_tile_kernel<9><<<grid, threads, smem, s>>>(batch, cin, H, W, tile_px, cout, act, slope, out_mul, splits);
-    }
-    if (splits > 1) {
-        dim3 rgrid((unsigned)(((long long)npix * cout + 255) / 256), n);
-        conv_reduce_kernel<<<rgrid, 256, 0, s>>>(batch, npix, cout, cpad, splits, act, slope, out_mul);
-        return launched(2);
-    }
-    return launched(1);
-}
-
-static bool problem_ok(const ojdf_conv_problem &q, int cin, int cout)
-{
-    return q.in_dev && q.weights_dev && q.scale_dev && q.shift_dev && q.out_dev && !(q.in_stride & 3) &&
-           q.in_stride >= ((cin + 3) & ~3) && q.out_stride >= q.out_coffset + cout && q.out_coffset >= 0 && q.dilation >= 1 &&
-           (!q.residual_dev || q.residual_stride >= cout) && q.in_step <= 1 && q.out_step <= 1;
-}
-
-extern "C" int ojdf_conv_nhwc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H,
-                                      int W, int taps, int act, float slope, float out_mul, float *scratch_dev,
-                                      size_t scratch_bytes, void *stream)
-{
-    if (!problems_host || n_problems < 1 || n_problems > kMaxBatch || cin < 1 || cout < 1 || H < 1 || W < 1 ||
-        H > 32767 || W > 32767 || (taps != 1 && taps != 9) || act < 0 || act > 4)
-        return OJDF_ERR_BADARG;
-    ConvBatch b;
-    for (int i = 0; i < kMaxBatch; ++i) {
-        const ojdf_conv_problem &q = problems_host[i < n_problems ? i : 0];
-        if (i < n_problems && !problem_ok(q, cin, cout)) return OJDF_ERR_BADARG;
-        b.p[i] = ConvProblem{q.in_dev, q.weights_dev, q.scale_dev, q.shift_dev, q.out_dev, q.residual_dev, nullptr,
-                             q.in_stride, q.out_stride, q.out_coffset, q.dilation, q.residual_stride};
-    }
-    return launch_conv(b, n_problems, cin, cout, H, W, taps, act, slope, out_mul, scratch_dev, scratch_bytes,
-                       (cudaStream_t)stream);
-}
-
-extern "C" int ojdf_conv_nhwc(const float *in_dev, int in_stride, int cin, int H, int W, int taps, int dilation,
-                              const float *weights_dev, const float *scale_dev, const float *shift_dev, int cout,
-                              int act, float slope, float out_mul, float *out_dev, int out_stride, int out_coffset,
-                              void *stream)
-{
-    ojdf_conv_problem q = {in_dev, weights_dev, scale_dev, shift_dev, out_dev, nullptr, in_stride, out_stride, out_coffset,
-                           dilation, 0, 0, 0, 0, 0, 0};
-    return ojdf_conv_nhwc_batched(&q, 1, cin, cout, H, W, taps, act, slope, out_mul, nullptr, 0, stream);
-}
 
 extern "C" int ojdf_avgpool3_nhwc(const float *in_dev, int in_stride, int H, int W, int C, float *out_dev, int out_stride,
                                   void *stream)

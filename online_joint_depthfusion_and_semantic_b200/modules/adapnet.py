@@ -277,8 +277,7 @@ class AdapNet(EngineOwner, nn.Module):
         return self._whole_engine(mod1).forward(mod1, mod2)
 
     def whole_engine_ready(self, mod1):
-        from .fusion_engine import conv_mode
-        return self.engine_ready(mod1) and self.whole_engine and conv_mode() == 'tc' and mod1.shape[0] == 1
+        return self.engine_ready(mod1) and self.whole_engine and mod1.shape[0] == 1
 
     def segment(self, mod1, mod2=None):
         """(scores f32, ids u8, (1 + id) / n_classes f32), each (1,h,w): the per-pixel maximum / arg-max of

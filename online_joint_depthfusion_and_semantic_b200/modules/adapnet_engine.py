@@ -1,27 +1,27 @@
-"""Inference engines for AdapNet++ on libojdf's tap-GEMM kernels.
+"""Inference engines for AdapNet++ on libojdf's tensor-core tap-GEMM kernels.
 
-`AdapNetEngine` (bottom of this file) runs the whole network pixel-major: everything except the 7x7 stem,
-the max-pool and the (optional) bilinear aux heads is a fused conv + BatchNorm + activation (+ residual)
-launch of the tensor-core kernel (csrc/ojdf_conv_tc.cu); stride-2 layers are the stride-1 layer followed by a
-consumer that reads every other pixel (`in_step = 2`); the three transposed convolutions are 4 / 16 phase
-convolutions that write every 2nd / 4th output pixel (`out_step`, dead taps masked).  It embeds
-`EncoderTailEngine`, described next.
+`AdapNetEngine` (bottom of this file) runs the whole network pixel-major: the 7x7 stem + BatchNorm + ReLU + max-pool is
+one own kernel (ojdf_adapnet_stem), everything else except the (optional) bilinear aux heads and the two tiny skip-join
+gates is a fused conv + BatchNorm + activation (+ residual) launch (csrc/ojdf_conv_tc.cu / ojdf_conv_ss.cu); stride-2
+layers are the stride-1 layer followed by a consumer that reads every other pixel (`in_step = 2`); the three transposed
+convolutions are 4 / 16 phase convolutions that write every 2nd / 4th output pixel (`out_step`, dead taps masked); the
+SSMA gate multiplies inside the epilogue of its sigmoid convolution; `segment()` adds the fused softmax / max / arg-max
+kernel.  It embeds `EncoderTailEngine`, described next.
 
 Low-resolution tail:
 
-At 240x320 the encoder runs layer3[1:], layer4 and the eASPP head on 15x20 feature maps with 256..2048
-channels (modules/adapnet.py:103-149,152-216).  That is 72 % of each encoder's FLOPs, and exactly the
-regime where the library's fp32 convolutions collapse (300 pixels cannot fill 148 SMs: 2.5 TFLOP/s
-measured).  Here these layers run pixel-major on `conv_tile_kernel` with the K loop split across
-blocks, BatchNorm / bias / ReLU / the residual add fused into the epilogue, the conv2a|conv2b and
-eASPP concatenations as channel offsets, eASPP's pooled branch folded into a bias, and both
-encoders (RGB + depth) batched into the same launches.
+At 240x320 the encoder runs layer3[1:], layer4 and the eASPP head on 15x20 feature maps with 256..2048 channels
+(modules/adapnet.py:103-149,152-216).  That is 72 % of each encoder's FLOPs, and exactly the regime where the library's
+fp32 convolutions collapse (300 pixels cannot fill 148 SMs: 2.5 TFLOP/s measured).  Here these layers split their K loop
+over CTAs, BatchNorm / bias / ReLU / the residual add are fused into the epilogue, the conv2a|conv2b and eASPP
+concatenations are channel offsets, eASPP's pooled branch is folded into a bias (computed on a side stream), and both
+encoders (RGB + depth) are batched into the same launches.  `EncoderTailEngine` can also run alone (AdapNet.whole_engine =
+False): the front and the decoder then stay on the module's torch forward and two tiny transposes hand the (C,15,20)
+tensor over.
 
-Everything before (conv1 .. layer3[0], the two skip convs) and after (SSMA, decoder) stays on the
-module's torch forward; two tiny transposes hand the (C,15,20) tensor over.  The eval-time-active
-bottleneck dropout of the reference (modules/adapnet.py:80-82) is applied between launches with
+The eval-time-active bottleneck dropout of the reference (modules/adapnet.py:80-82) is applied between launches with
 torch's own dropout, so its random stream is the library's in both paths.
-Eval mode + no_grad only; rebuilt when parameters may have changed (same rules as FusionNetEngine).
+Eval mode + no_grad only; rebuilt when parameters may have changed (modules/_engine_cache.py).
 """
 import functools
 
@@ -32,7 +32,7 @@ from .. import _lib
 
 import ctypes as C
 
-from .fusion_engine import ConvProblem, _Conv as _ConvBase, _pad4, conv_mode
+from .fusion_engine import ConvProblem, _Conv as _ConvBase, _pad4
 
 
 class StemProblem(C.Structure):
@@ -41,13 +41,6 @@ class StemProblem(C.Structure):
                 ('out_dev', C.c_void_p), ('out_stride', C.c_int), ('out_coffset', C.c_int)]
 
 _TAIL_PIXELS = 300          # 15 x 20: four 128-pixel M-tiles per problem
-
-
-def _npad_for(cout, n_problems, n_tiles=4):
-    """Output-channel group width of the tensor-core kernel.  The default grouping (<= 128 channels per CTA)
-    is right everywhere now that small maps split their K loop over CTAs (scratch argument); narrower
-    groups only re-read and re-split the same activations."""
-    return 0
 
 
 def deconv_phase_weights(weight, stride, padding):
@@ -76,9 +69,7 @@ def deconv_phase_weights(weight, stride, padding):
 
 
 def _Conv(conv, bn, act, device, n_problems=2, n_tiles=4, **kw):
-    tc = conv_mode() == 'tc'
-    return _ConvBase(conv, bn, act, device, tc=tc,
-                     npad_req=_npad_for(conv.out_channels, n_problems, n_tiles) if tc else 0, **kw)
+    return _ConvBase(conv, bn, act, device, npad_req=0, **kw)
 
 
 class _Unit:
@@ -143,7 +134,6 @@ class EncoderTailEngine:
         self.partial = torch.empty(self.PARTIAL_BLOCKS * 2048, dtype=torch.float32, device=dev)
         self._keep += [T1, T2, D]
         self.plan = []
-        self.tc = conv_mode() == 'tc'
 
         def conv_step(pairs):
             c0 = pairs[0][0]
@@ -211,12 +201,8 @@ class EncoderTailEngine:
             kind = step[0]
             if kind == 'conv':
                 _, arr, n, cin, cout, taps, act, slope, npad_req = step
-                if self.tc:
-                    _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, self.flags,
-                                                      self.scratch.data_ptr(), self.scratch.numel() * 4, st))
-                else:
-                    _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0,
-                                                        self.scratch.data_ptr(), self.scratch.numel() * 4, st))
+                _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, self.flags,
+                                                  self.scratch.data_ptr(), self.scratch.numel() * 4, st))
             elif kind == 'dropout':
                 for t in step[1]:                            # reference quirk: active in eval mode
                     t.copy_(F.dropout(t, p=0.5, training=True))
@@ -265,9 +251,6 @@ class AdapNetEngine:
         (H4, W4), (H8, W8), (H16, W16) = (h // 4, w // 4), (h // 8, w // 8), (h // 16, w // 16)
         N4, N8, N16 = H4 * W4, H8 * W8, H16 * W16
         self.dims = (H4, W4, H8, W8, H16, W16)
-        self.tc = conv_mode() == 'tc'
-        if not self.tc:
-            raise NotImplementedError('the whole-network engine needs the tensor-core kernel (strided reads)')
         self._keep, self.plan = [], []
         plan = self.plan
 

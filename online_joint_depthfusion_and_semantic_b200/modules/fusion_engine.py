@@ -29,7 +29,6 @@ from torch import nn
 
 from .. import _lib
 
-_GROUP = 20
 _ACT = {'none': 0, 'relu': 1, 'lrelu': 2, 'tanh': 3, 'sigmoid': 4, 'sigmoid_mul': 5}
 
 
@@ -41,13 +40,6 @@ def group_map(n_groups, width):
     """Positions of n_groups x width real channels when every group is padded to a multiple of 4."""
     pitch = _pad4(width)
     return [g * pitch + c for g in range(n_groups) for c in range(width)], n_groups * pitch
-
-
-def conv_mode():
-    """'tc' (default): tcgen05 3xTF32 tap GEMM (csrc/ojdf_conv_tc.cu); 'fma': the fp32 FMA kernels."""
-    m = os.environ.get('OJDF_CONV', 'tc')
-    assert m in ('tc', 'fma'), m
-    return m
 
 
 def pack_tc_weights(w, npad_req=0):
@@ -76,9 +68,9 @@ class PoolProblem(C.Structure):
 
 
 class _Conv:
-    """One fused conv (+BN) (+activation): weights re-laid out for conv_tile_kernel."""
+    """One fused conv (+BN) (+activation): weights packed for the tensor-core kernels, BatchNorm folded on the host in f64."""
 
-    def __init__(self, conv, bn, act, device, cin_slice=None, slope=0.01, tc=None, cin_map=None, npad_req=0, raw=False):
+    def __init__(self, conv, bn, act, device, cin_slice=None, slope=0.01, cin_map=None, npad_req=0, raw=False):
         w = conv.weight.detach().double().cpu()                 # (cout, cin, kh, kw); all folding on the host in f64
         if cin_slice is not None:
             w = w[:, cin_slice[0]:cin_slice[1]]
@@ -93,12 +85,6 @@ class _Conv:
         self.taps, self.cin, self.cout = kh * kw, cin, cout
         self.dil = int(conv.dilation[0])
         assert kh == 1 or int(conv.padding[0]) == self.dil
-        groups, cin_p = (cout + _GROUP - 1) // _GROUP, (cin + 7) // 8 * 8
-        prep = torch.zeros(groups, self.taps, cin_p, _GROUP, dtype=torch.float64)
-        wt = w.permute(2, 3, 1, 0).reshape(self.taps, cin, cout)             # [tap][ci][co], tap = ky*3+kx
-        for g in range(groups):
-            n = min(_GROUP, cout - g * _GROUP)
-            prep[g, :, :cin, :n] = wt[:, :, g * _GROUP:g * _GROUP + n]
         bias = conv.bias.detach().double().cpu() if conv.bias is not None else torch.zeros(cout, dtype=torch.float64)
         if bn is not None:
             s = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
@@ -107,17 +93,15 @@ class _Conv:
             s, t = torch.ones(cout, dtype=torch.float64), bias
         if raw:                                                # the bare product W.x: bias / BatchNorm / activation applied later
             s, t, act = torch.ones(cout, dtype=torch.float64), torch.zeros(cout, dtype=torch.float64), 'none'
-        self.weights = prep.float().contiguous().to(device)
         self.npad_req = int(npad_req)
-        self.weights_tc = pack_tc_weights(w, self.npad_req).to(device) if (conv_mode() == 'tc' if tc is None else tc) else None
+        self.weights_tc = pack_tc_weights(w, self.npad_req).to(device)
         self.scale = s.float().contiguous().to(device)
         self.shift = t.float().contiguous().to(device)
         self.act, self.slope = _ACT[act], float(slope)
 
     def problem(self, src, src_stride, dst, dst_stride, dst_off=0, shift=None, residual=None, residual_stride=0,
                 in_step=0, in_width=0, out_step=0, out_width=0, tap_mask=0, dst_ptr_offset=0):
-        wts = self.weights_tc if self.weights_tc is not None else self.weights
-        return ConvProblem(src.data_ptr(), wts.data_ptr(), self.scale.data_ptr(),
+        return ConvProblem(src.data_ptr(), self.weights_tc.data_ptr(), self.scale.data_ptr(),
                            (self.shift if shift is None else shift).data_ptr(), dst.data_ptr() + 4 * dst_ptr_offset,
                            None if residual is None else residual.data_ptr(), src_stride, dst_stride, dst_off, self.dil,
                            residual_stride, in_step, in_width, out_step, out_width, tap_mask)
@@ -200,7 +184,6 @@ class FusionNetEngine:
         self._keep = [heads, tail]                              # owns every device tensor the plan points at
         self.partial = torch.empty(self.PARTIAL_BLOCKS * 256, dtype=torch.float32, device=dev)
         self.plan = []
-        self.tc = conv_mode() == 'tc'
         self.side = None
         self.flags = 1 | int(getattr(net, 'conv_flags', 0))        # 1: the pad channels are ours; 64: 1xTF32 (precision 'fast')
 
@@ -319,10 +302,7 @@ class FusionNetEngine:
                 if kind == 'conv':
                     _, arr, n, cin, cout, taps, act, slope = step[:8]
                     out_mul = step[8] if len(step) > 8 else 1.0
-                    if self.tc:
-                        _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, 0, self.flags, None, 0, st))
-                    else:
-                        _lib.check(L.ojdf_conv_nhwc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, None, 0, st))
+                    _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, 0, self.flags, None, 0, st))
                 elif kind == 'pools':
                     _, arr, n, ch = step
                     _lib.check(L.ojdf_avgpool3_batched(arr, n, H, W, ch, 1, st))

@@ -13,6 +13,8 @@ integrator are one libojdf call each, and the update handed to the integrator is
 `FrameUpdate` (per-ray record + network output + masked depth) instead of ~100 MB of gathered
 indices / weights / values (modules/pipeline.py:150-169).
 """
+import os
+
 import torch
 from torch import nn
 
@@ -48,7 +50,8 @@ class Pipeline(nn.Module):
         self._extractor = Extractor(config)
         self._integrator = Integrator(config)
         self.use_cuda_graphs = True          # replay the fixed-shape networks as CUDA graphs in inference
-        self.plan_ahead = True               # issue the geometry half of the integration on a side stream, early
+        # issue the geometry half of the integration on a side stream, early (OJDF_PLAN_AHEAD=0: plan + apply after FusionNet)
+        self.plan_ahead = os.environ.get('OJDF_PLAN_AHEAD', '1') != '0'
         self._seg_graph = None
         self._seg_graph_token = (None, None)
         self._seg_graph_fn = None

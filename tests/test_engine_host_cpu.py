@@ -38,16 +38,42 @@ def test_group_map_and_zero_weight_rows():
     conv = torch.nn.Conv2d(57, 19, 1)
     bn = torch.nn.BatchNorm2d(19).eval()
     bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 1.5); bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_()
-    c = _Conv(conv, bn, 'none', 'cpu', tc=False, cin_map=(pos, width))
+    c = _Conv(conv, bn, 'none', 'cpu', cin_map=(pos, width))
     assert c.cin == 60 and c.cout == 19 and c.taps == 1
     x = torch.randn(1, 57, 6, 5)
     ref = bn(conv(x)).detach()[0].permute(1, 2, 0).reshape(30, 19)
     xp = torch.full((30, 60), 1234.5)                          # garbage in the pad channels
     xp[:, pos] = x[0].permute(1, 2, 0).reshape(30, 57)
-    prep = c.weights[0, 0]                                     # [cin padded to 8][20], output group 0
-    got = (xp @ prep[:60, :19]) * c.scale + c.shift
+    wmat = _unpack_tc(c.weights_tc, 60, 19, 1)[0]              # (cout, cin) = hi + lo of the packed images, tap 0
+    got = (xp.double() @ wmat.t().double()).float() * c.scale + c.shift
     assert float((got - ref).abs().max()) < 1e-4 * float(ref.abs().max())
-    assert float(prep[[19, 39, 59]].abs().max()) == 0.0
+    assert float(wmat[:, [19, 39, 59]].abs().max()) == 0.0     # zero weights at the pad channels
+
+
+def _unpack_tc(packed, cin, cout, taps):
+    """Inverse of ojdf_conv_tc_pack_weights (include/ojdf.h): [group][tap][K chunk of 32][hi | lo][npad rows][32 floats],
+    16-byte chunk c of row r stored at chunk c ^ (r & 7); returns (taps, cout, cin) = hi + lo."""
+    import ctypes as C
+    from online_joint_depthfusion_and_semantic_b200 import _lib
+    npad, groups = C.c_int(), C.c_int()
+    _lib.check(_lib.lib().ojdf_conv_tc_layout(cout, 0, C.byref(npad), C.byref(groups)))
+    npad, groups = npad.value, groups.value
+    nkc = (cin + 31) // 32
+    img = packed.reshape(groups, taps, nkc, 2, npad, 32)
+    out = torch.zeros(taps, cout, cin)
+    for g in range(groups):
+        for r in range(npad):
+            co = g * npad + r
+            if co >= cout:
+                continue
+            for kc in range(nkc):
+                for k in range(32):
+                    ci = kc * 32 + k
+                    if ci >= cin:
+                        continue
+                    col = ((k >> 2) ^ (r & 7)) * 4 + (k & 3)
+                    out[:, co, ci] = img[g, :, kc, 0, r, col] + img[g, :, kc, 1, r, col]
+    return out
 
 
 def test_average_pools_commute_with_the_1x1_convolution():
