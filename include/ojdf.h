@@ -206,6 +206,34 @@ int ojdf_conv_tc_pack_weights(const float *w_host, int cin, int cout, int taps, 
 int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W,
                          int taps, int act, float slope, float out_mul, int npad_req, int flags, float *scratch_dev,
                          size_t scratch_bytes, void *stream);
+/* ---- a10: chains of 1x1 convolutions kept on chip (csrc/ojdf_conv_chain.cu) --------------------------------------
+ * FusionNet's Pred stack (modules/model.py:24-52: eleven 1x1 conv + BatchNorm + LeakyReLU layers, 114 -> ... -> 9) and the
+ * end of every VortexPooling block (modules/model.py:131-141,157-159: four 19 -> 114 conv + BN + ReLU whose concatenation
+ * feeds the 456 -> 114 `final` conv) as ONE launch each: a 128-pixel tile walks all steps inside a CTA, the activated
+ * output of a step is split into tf32 hi / lo and written back to tensor memory as the A operand of the next step, so
+ * activations never leave the SM between layers (same 3xTF32 numerics as ojdf_conv_tc_batched).
+ *   step = D[acc] (+)= A . W^T  (cout <= 128), A = input `src` (a pixel-major global buffer, any cin) or, with src = -1,
+ *   the activated output of the previous "epi = 1" step (then cin must equal that step's cout);
+ *   fresh = 1 overwrites accumulator `acc` (0 or 1), fresh = 0 adds to it (sum over concatenated inputs);
+ *   epi = 0: nothing (a later step adds to the same accumulator), 1: act(scale * D + shift) -> next step's A,
+ *   2: out = out_mul * act(scale * D + shift) -> out_dev (the last step, and only the last step).
+ * Up to 2 problems of identical shape per launch (the two FusionNet heads): pointer arrays are indexed by problem.
+ * weights: ojdf_conv_tc_pack_weights(taps = 1, npad_req = 0) images.  flags: 1 = the caller owns the pad channels of
+ * the output rows (TMA-store epilogue for widths that are not a multiple of 4), 8 = per-thread stores, 64 = 1xTF32. */
+typedef struct ojdf_chain_input {
+    const float *in_dev[2];         /* (H*W, in_stride) f32 per problem, 16-byte aligned */
+    int in_stride, cin;             /* in_stride % 4 == 0; channels [0, cin) are read */
+} ojdf_chain_input;
+typedef struct ojdf_chain_step {
+    const float *weights_dev[2];
+    const float *scale_dev[2];
+    const float *shift_dev[2];      /* scale / shift: cout floats, read by epi = 1 / 2 steps */
+    int src, cin, cout, acc, fresh, epi, act;
+    float slope;
+} ojdf_chain_step;
+int ojdf_conv_chain(const ojdf_chain_input *inputs_host, int n_inputs, const ojdf_chain_step *steps_host, int n_steps,
+                    int n_problems, int H, int W, float *const *out_dev_host, const int *out_coffset_host, int out_stride,
+                    float out_mul, int flags, void *stream);
 /* ---- a17 / a3: the two ends of AdapNet++ that are not tap GEMMs (csrc/ojdf_adapnet_aux.cu) ------
  * ojdf_adapnet_stem: ResNet-50 conv1 7x7 / 2 / pad 3 (3 -> 64) + BatchNorm(eval, folded into scale/shift) + ReLU +
  * max-pool 3x3 / 2 / pad 1 (modules/adapnet.py:101,134-137) in one kernel: in_dev (3,H,W) f32 NCHW, weights_dev
@@ -248,11 +276,19 @@ int ojdf_vortex_bias(const float *in_dev, int in_stride, int npix, int C, const 
                      const float *f_scale_dev, const float *f_shift_dev, int Cout, float *partial_dev,
                      int partial_blocks, float *shift_out_dev, void *stream);
 /* Generalisation used by AdapNet++'s eASPP branch 5 (modules/adapnet.py:201-205): C <= 2048 and an
- * optional ReLU on the pooled branch (v_relu). */
+ * optional ReLU on the pooled branch (v_relu).  Wide branches (C * Cg >= 65536) spread the first matrix-vector product
+ * over many blocks and keep one C-float block of the scratch for its result. */
 int ojdf_gap_bias(const float *in_dev, int in_stride, int npix, int C, const float *wg_dev,
                   const float *g_scale_dev, const float *g_shift_dev, int Cg, int v_relu, const float *wf1_dev,
                   const float *f_scale_dev, const float *f_shift_dev, int Cout, float *partial_dev,
                   int partial_blocks, float *shift_out_dev, void *stream);
+/* Decoder skip join of AdapNet++ (modules/adapnet.py:305-315): gate[c] = relu(b[c] + W[c,:] . mean_pixels(x[:, :C])) from the
+ * C (<= 1024, % 4 == 0) decoder features x (npix, x_stride), out[p, c] = skip[p, c] * gate[c] for the Cg (<= 32) skip
+ * channels -- torch.mean + conv + relu + multiply + the copy into the concatenated buffer in two launches.
+ * w_dev: (Cg, C) f32, b_dev: (Cg); partial_dev: scratch of partial_blocks*C floats. */
+int ojdf_adapnet_skip_join(const float *x_dev, int x_stride, int C, int npix, const float *w_dev, const float *b_dev,
+                           int Cg, const float *skip_dev, int skip_stride, float *out_dev, int out_stride,
+                           float *partial_dev, int partial_blocks, void *stream);
 /* (C, npix) fp32 <-> pixel-major (npix, stride) with a channel offset: hand-over between NCHW tensors
  * and the pixel-major kernels. */
 int ojdf_nchw_to_nhwc(const float *in_dev, int C, int npix, float *out_dev, int out_stride, int out_coffset,

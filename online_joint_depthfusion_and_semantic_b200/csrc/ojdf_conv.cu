@@ -250,6 +250,103 @@ gap_bias_kernel(const float *__restrict__ partial, int nblocks, int npix, int C,
     }
 }
 
+// Wide pooled branches (eASPP: C = 2048, Cg = 256 -- 2 MB of weights): the first matrix-vector product on many blocks.
+// Block b folds the partial sums into the mean vector (fixed order) and computes 8 outputs, one per warp:
+// v[o] = act(g_scale[o] * (wg[o,:] . mean) + g_shift[o]).
+__global__ void __launch_bounds__(256)
+gap_v_kernel(const float *__restrict__ partial, int nblocks, int npix, int C, const float *__restrict__ wg,
+             const float *__restrict__ g_scale, const float *__restrict__ g_shift, int Cg, int v_relu, float *__restrict__ v_out)
+{
+    __shared__ float s_mean[2048];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int c = t; c < C; c += blockDim.x) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int b = 0;
+        for (; b + 3 < nblocks; b += 4) {
+            s0 += partial[(size_t)b * C + c];
+            s1 += partial[(size_t)(b + 1) * C + c];
+            s2 += partial[(size_t)(b + 2) * C + c];
+            s3 += partial[(size_t)(b + 3) * C + c];
+        }
+        for (; b < nblocks; ++b) s0 += partial[(size_t)b * C + c];
+        s_mean[c] = ((s0 + s1) + (s2 + s3)) / (float)npix;
+    }
+    __syncthreads();
+    const int o = blockIdx.x * 8 + warp;
+    if (o >= Cg) return;
+    const float *w = wg + (size_t)o * C;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int c = lane;
+    for (; c + 96 < C; c += 128) {
+        a0 = fmaf(__ldg(w + c), s_mean[c], a0);
+        a1 = fmaf(__ldg(w + c + 32), s_mean[c + 32], a1);
+        a2 = fmaf(__ldg(w + c + 64), s_mean[c + 64], a2);
+        a3 = fmaf(__ldg(w + c + 96), s_mean[c + 96], a3);
+    }
+    for (; c < C; c += 32) a0 = fmaf(__ldg(w + c), s_mean[c], a0);
+    float a = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+    if (lane == 0) {
+        a = fmaf(a, g_scale[o], g_shift[o]);
+        v_out[o] = v_relu ? fmaxf(a, 0.0f) : a;
+    }
+}
+// ... and the second one: shift_out[o] = f_shift[o] + f_scale[o] * (wf1[o,:] . v), one output per warp.
+__global__ void __launch_bounds__(1024)
+gap_shift_kernel(const float *__restrict__ v, int Cg, const float *__restrict__ wf1, const float *__restrict__ f_scale,
+                 const float *__restrict__ f_shift, int Cout, float *__restrict__ shift_out)
+{
+    __shared__ float s_v[256];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
+    if (t < Cg) s_v[t] = v[t];
+    __syncthreads();
+    for (int o = warp; o < Cout; o += nwarps) {
+        float a = 0.0f;
+        for (int c = lane; c < Cg; c += 32) a = fmaf(__ldg(wf1 + (size_t)o * Cg + c), s_v[c], a);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+        if (lane == 0) shift_out[o] = fmaf(a, f_scale[o], f_shift[o]);
+    }
+}
+
+// Decoder._join of AdapNet++ (modules/adapnet.py:305-315): gate[c] = relu(b[c] + W[c,:] . mean_pixels(x)) (24 channels from
+// the 256 decoder features), out[p, c] = skip[p, c] * gate[c].  Every block folds the partial channel sums and computes
+// the (tiny) gate itself, then scales its share of the pixels.  C <= 1024, Cg <= 32.
+__global__ void __launch_bounds__(256)
+skip_gate_kernel(const float *__restrict__ partial, int nblocks, int npix, int C, const float *__restrict__ w,
+                 const float *__restrict__ b, int Cg, const float *__restrict__ skip, int skip_stride, float *__restrict__ out,
+                 int out_stride)
+{
+    __shared__ float s_mean[1024];
+    __shared__ float s_gate[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int c = t; c < C; c += blockDim.x) {
+        float s0 = 0.f, s1 = 0.f;
+        int k = 0;
+        for (; k + 1 < nblocks; k += 2) {
+            s0 += partial[(size_t)k * C + c];
+            s1 += partial[(size_t)(k + 1) * C + c];
+        }
+        if (k < nblocks) s0 += partial[(size_t)k * C + c];
+        s_mean[c] = (s0 + s1) / (float)npix;
+    }
+    __syncthreads();
+    for (int o = warp; o < Cg; o += 8) {
+        float a = 0.0f;
+        for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w + (size_t)o * C + c), s_mean[c], a);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+        if (lane == 0) s_gate[o] = fmaxf(a + b[o], 0.0f);
+    }
+    __syncthreads();
+    const long long n = (long long)npix * Cg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + t; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i / Cg), c = (int)(i - (long long)p * Cg);
+        out[(size_t)p * out_stride + c] = skip[(size_t)p * skip_stride + c] * s_gate[c];
+    }
+}
+
 // Network input assembly (modules/pipeline.py:74-102 + modules/model.py:269,274): pixel-major
 // [values(P) | weights(P) | last channel] into channel offset 0 of a buffer with `stride` floats per
 // pixel; head A's last channel is the depth frame, head B's (optional) the normalised label frame.
@@ -368,14 +465,44 @@ extern "C" int ojdf_gap_bias(const float *in_dev, int in_stride, int npix, int C
     int pb = npix / 128;
     if (pb < 8) pb = 8;
     if (pb > 148) pb = 148;
-    if (pb > partial_blocks) pb = partial_blocks;
+    // wide branches (eASPP: 2048 x 256 weights) spread the first matrix-vector product over Cg / 8 blocks; its result lives
+    // in one more C-float block of the scratch
+    const bool wide = (long long)C * Cg >= 65536 && partial_blocks >= 2 && Cg <= C;
+    if (pb > partial_blocks - (wide ? 1 : 0)) pb = partial_blocks - (wide ? 1 : 0);
     if (pb > npix) pb = npix;
     if (!(C & 3) && C <= 1024 && !(in_stride & 3) && !((uintptr_t)in_dev & 15))
         channel_sum4_kernel<<<pb, 256, 0, s>>>(in_dev, in_stride, npix, C, partial_dev);
     else
         channel_sum_kernel<<<dim3(pb, (C + 255) / 256), 256, 0, s>>>(in_dev, in_stride, npix, C, partial_dev);
+    if (wide) {
+        float *v = partial_dev + (size_t)pb * C;                // the block of the scratch kept free above
+        gap_v_kernel<<<(Cg + 7) / 8, 256, 0, s>>>(partial_dev, pb, npix, C, wg_dev, g_scale_dev, g_shift_dev, Cg, v_relu, v);
+        gap_shift_kernel<<<1, 1024, 0, s>>>(v, Cg, wf1_dev, f_scale_dev, f_shift_dev, Cout, shift_out_dev);
+        return launched(3);
+    }
     gap_bias_kernel<<<1, 1024, 0, s>>>(partial_dev, pb, npix, C, wg_dev, g_scale_dev, g_shift_dev, Cg, v_relu, wf1_dev,
                                      f_scale_dev, f_shift_dev, Cout, shift_out_dev);
+    return launched(2);
+}
+
+extern "C" int ojdf_adapnet_skip_join(const float *x_dev, int x_stride, int C, int npix, const float *w_dev, const float *b_dev,
+                                      int Cg, const float *skip_dev, int skip_stride, float *out_dev, int out_stride,
+                                      float *partial_dev, int partial_blocks, void *stream)
+{
+    if (!x_dev || !w_dev || !b_dev || !skip_dev || !out_dev || !partial_dev || npix < 1 || C < 4 || C > 1024 || (C & 3) ||
+        (x_stride & 3) || x_stride < C || ((uintptr_t)x_dev & 15) || Cg < 1 || Cg > 32 || skip_stride < Cg || out_stride < Cg ||
+        partial_blocks < 1)
+        return OJDF_ERR_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int pb = npix / 128;
+    if (pb < 8) pb = 8;
+    if (pb > 148) pb = 148;
+    if (pb > partial_blocks) pb = partial_blocks;
+    if (pb > npix) pb = npix;
+    channel_sum4_kernel<<<pb, 256, 0, s>>>(x_dev, x_stride, npix, C, partial_dev);
+    int blocks = (int)(((long long)npix * Cg + 2047) / 2048);
+    if (blocks > 148) blocks = 148;
+    skip_gate_kernel<<<blocks, 256, 0, s>>>(partial_dev, pb, npix, C, w_dev, b_dev, Cg, skip_dev, skip_stride, out_dev, out_stride);
     return launched(2);
 }
 

@@ -252,6 +252,7 @@ class AdapNetEngine:
         N4, N8, N16 = H4 * W4, H8 * W8, H16 * W16
         self.dims = (H4, W4, H8, W8, H16, W16)
         self._keep, self.plan = [], []
+        self._join_w = {}
         plan = self.plan
 
         def z(npix, c):
@@ -394,6 +395,10 @@ class AdapNetEngine:
 
         d = net.decoder
         C = int(d.n_classes)
+        for conv in (d.fuse_conv1, d.fuse_conv2):               # gate of the skip joins: (24, 256) weights + bias
+            assert conv.out_channels == 24 and conv.in_channels == 256
+            self._join_w[id(conv)] = (conv.weight.detach().reshape(24, 256).float().contiguous().to(dev),
+                                      conv.bias.detach().float().contiguous().to(dev))
         if self.stage2:
             self.skip2 = ssma(net.ssma_s2, self.SK2, N4, H4, W4, 24)
             self.skip1 = ssma(net.ssma_s1, self.SK1, N8, H8, W8, 24)
@@ -473,12 +478,13 @@ class AdapNetEngine:
         return self.seg_scores, self.seg_ids, self.seg_frame
 
     def _join(self, x, skip, conv, J, H, W):
-        """Decoder._join (modules/adapnet.py:305-315): [x | gate * skip] into the 280-channel buffer J."""
+        """Decoder._join (modules/adapnet.py:305-315): [x | gate * skip] into the 280-channel buffer J; channels [0, 256)
+        already hold x.  The gate (global mean -> 1x1 conv -> ReLU) and the multiply are two launches of libojdf."""
         d = self.net.decoder
-        Jv = J.view(1, H, W, 280)                               # channels [0, 256) already hold x
-        sk = skip.view(1, H, W, 24)
         if d.fusion:
-            gate = torch.relu(conv(F.adaptive_avg_pool2d(x, 1))).reshape(1, 1, 1, 24)
-            Jv[..., 256:].copy_(sk * gate)
+            w, b = self._join_w[id(conv)]
+            _lib.check(_lib.lib().ojdf_adapnet_skip_join(J.data_ptr(), 280, 256, H * W, w.data_ptr(), b.data_ptr(), 24, skip.data_ptr(), 24,
+                                                         J.data_ptr() + 4 * 256, 280, self.tail.partial.data_ptr(), self.tail.PARTIAL_BLOCKS,
+                                                         _lib.stream_ptr(self.device)))
         else:
-            Jv[..., 256:].copy_(sk)
+            J.view(1, H, W, 280)[..., 256:].copy_(skip.view(1, H, W, 24))
