@@ -61,6 +61,23 @@ class ConvProblem(C.Structure):
                 ('in_width', C.c_int), ('out_step', C.c_int), ('out_width', C.c_int), ('tap_mask', C.c_int)]
 
 
+class ChainInput(C.Structure):
+    """include/ojdf.h: ojdf_chain_input."""
+    _fields_ = [('in_dev', C.c_void_p * 2), ('in_stride', C.c_int), ('cin', C.c_int)]
+
+
+class ChainStep(C.Structure):
+    """include/ojdf.h: ojdf_chain_step."""
+    _fields_ = [('weights_dev', C.c_void_p * 2), ('scale_dev', C.c_void_p * 2), ('shift_dev', C.c_void_p * 2), ('src', C.c_int),
+                ('cin', C.c_int), ('cout', C.c_int), ('acc', C.c_int), ('fresh', C.c_int), ('epi', C.c_int), ('act', C.c_int),
+                ('slope', C.c_float)]
+
+
+def _ptrs(tensors):
+    """Two-slot pointer array of the chain structs (one slot per problem)."""
+    return (C.c_void_p * 2)(*([t.data_ptr() if t is not None else None for t in tensors] + [None] * (2 - len(tensors))))
+
+
 class PoolProblem(C.Structure):
     """include/ojdf.h: ojdf_pool_problem."""
     _fields_ = [('in_dev', C.c_void_p), ('out_dev', C.c_void_p), ('scale_dev', C.c_void_p), ('shift_dev', C.c_void_p),
@@ -128,6 +145,8 @@ class _Vortex:
         C_ = self.cout
         # the 4 branch outputs, each in its own 4-aligned group of the branch buffer
         self.final = _Conv(fin_conv, fin_bn, 'none', device, cin_slice=(C_, 5 * C_), cin_map=group_map(4, C_))
+        # the same convolution as four 114-column slices, one per branch (chain kernel: the concatenation becomes a sum)
+        self.final_b = [_Conv(fin_conv, fin_bn, 'none', device, cin_slice=(C_ * (1 + b), C_ * (2 + b))) for b in range(4)]
         # global branch: v1 = BN(conv(mean)); its share of the final conv becomes a bias
         wg = torch.zeros(C_, self.cin, dtype=torch.float32)
         wg[:, torch.as_tensor(in_map[0], dtype=torch.long)] = gp_conv.weight.detach().reshape(C_, -1).float().cpu()
@@ -186,6 +205,9 @@ class FusionNetEngine:
         self.plan = []
         self.side = None
         self.flags = 1 | int(getattr(net, 'conv_flags', 0))        # 1: the pad channels are ours; 64: 1xTF32 (precision 'fast')
+        # chains of 1x1 convolutions (the end of every vortex block, the Pred stack) as single launches that keep the
+        # activations in tensor memory (csrc/ojdf_conv_chain.cu); OJDF_CHAIN=0: layer by layer
+        self.chain = os.environ.get('OJDF_CHAIN', '1') != '0' and bool(getattr(net, 'use_chain', True))
 
         def conv_step(convs_problems):
             """convs_problems: list of (conv, problem) with identical shapes -> one batched launch."""
@@ -210,7 +232,8 @@ class FusionNetEngine:
             Y = [[None] + [z(mid_s) for _ in range(3)] for _ in range(n)]          # W_b . x, b = 1..3
             P1 = [[None, None] + [z(mid_s) for _ in range(2)] for _ in range(n)]   # pool(Y_b), b = 2, 3
             P2 = [z(mid_s) for _ in range(n)]                                       # pool(pool(Y_3))
-            br_out = [z(4 * Cvp) for _ in range(n)]
+            chained = self.chain and n <= 2 and Cv <= 128
+            br_out = [None if chained else z(4 * Cvp) for _ in range(n)]   # the chain launch never materialises the branch outputs
             self._keep += [tb, Y, P1, P2, br_out]
             # global-pool branch -> bias of the final conv: a long, thin reduction (two launches, one of them a single
             # block) that only the LAST conv of the vortex needs: it runs on a side stream next to the branch convolutions
@@ -236,6 +259,22 @@ class FusionNetEngine:
                        for i in range(n) for b in range(4)])
             conv_step([(vs[i].branches[b][2], vs[i].branches[b][2].problem(tb[i][b][1], mid_s, tb[i][b][0], mid_s))
                        for i in range(n) for b in range(4)])
+            if chained:
+                # branch-out convs + `final` as one chain launch: per branch 19 -> 114 (+BN+ReLU) stays in tensor memory and is
+                # multiplied by its 114-column slice of `final`, the four products add up in the second accumulator
+                self.plan.append(('join_bias',))
+                inputs = [ChainInput(_ptrs([tb[i][b][0] for i in range(n)]), mid_s, vs[0].branches[b][3].cin) for b in range(4)]
+                steps = []
+                for b in range(4):
+                    c3 = [vs[i].branches[b][3] for i in range(n)]
+                    steps.append(ChainStep(_ptrs([c.weights_tc for c in c3]), _ptrs([c.scale for c in c3]), _ptrs([c.shift for c in c3]),
+                                           b, c3[0].cin, Cv, 0, 1, 1, c3[0].act, c3[0].slope))
+                    fb = [vs[i].final_b[b] for i in range(n)]
+                    steps.append(ChainStep(_ptrs([c.weights_tc for c in fb]), _ptrs([c.scale for c in fb]),
+                                           _ptrs([vs[i].frame_shift for i in range(n)]), -1, Cv, fb[0].cout, 1, 1 if b == 0 else 0,
+                                           2 if b == 3 else 0, fb[0].act, fb[0].slope))
+                self.chain_step(inputs, steps, n, [d[0] for d in dsts], [d[2] for d in dsts], dsts[0][1], 1.0)
+                return
             conv_step([(vs[i].branches[b][3], vs[i].branches[b][3].problem(tb[i][b][0], mid_s, br_out[i], 4 * Cvp, b * Cvp))
                        for i in range(n) for b in range(4)])
             self.plan.append(('join_bias',))                     # the final conv reads the frame shifts computed on the side stream
@@ -257,12 +296,23 @@ class FusionNetEngine:
         pp = [z(Cs) for _ in range(2)]
         self._keep += [pred, pp]
         cur, cs = vout, Cs
+        if self.chain and all(c.cout <= 128 for c in pred) and len(pred) <= 12:
+            # the whole Pred stack as one chain launch: activations stay in tensor memory between the eleven layers
+            steps = [ChainStep(_ptrs([c.weights_tc]), _ptrs([c.scale]), _ptrs([c.shift]), 0 if i == 0 else -1, c.cin, c.cout, 0, 1,
+                               2 if i == len(pred) - 1 else 1, c.act, c.slope) for i, c in enumerate(pred)]
+            self.chain_step([ChainInput(_ptrs([vout]), Cs, pred[0].cin)], steps, 1, [self.est], [0], self.P, self.scale)
+            pred = []
         for i, c in enumerate(pred):
             last = i == len(pred) - 1
             dst, ds = (self.est, self.P) if last else (pp[i % 2], Cs)
             arr = (ConvProblem * 1)(c.problem(cur, cs, dst, ds, 0))
             self.plan.append(('conv', arr, 1, c.cin, c.cout, c.taps, c.act, c.slope, self.scale if last else 1.0))
             cur, cs = dst, ds
+
+    def chain_step(self, inputs, steps, nz, outs, coffs, out_stride, out_mul):
+        ia, sa = (ChainInput * len(inputs))(*inputs), (ChainStep * len(steps))(*steps)
+        op, oc = (C.c_void_p * nz)(*[o.data_ptr() for o in outs]), (C.c_int * nz)(*[int(c) for c in coffs])
+        self.plan.append(('chain', ia, len(inputs), sa, len(steps), nz, op, oc, int(out_stride), float(out_mul)))
 
     def pack_target(self, frame, sem_frame=None):
         """What Extractor.forward(pack=...) needs to write this engine's input rows itself: (buf_a, buf_b, last_a, last_b, stride)."""
@@ -303,6 +353,9 @@ class FusionNetEngine:
                     _, arr, n, cin, cout, taps, act, slope = step[:8]
                     out_mul = step[8] if len(step) > 8 else 1.0
                     _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, out_mul, 0, self.flags, None, 0, st))
+                elif kind == 'chain':
+                    _, ia, ni, sa, ns, nz, op, oc, ostride, omul = step
+                    _lib.check(L.ojdf_conv_chain(ia, ni, sa, ns, nz, H, W, op, oc, ostride, omul, self.flags, st))
                 elif kind == 'pools':
                     _, arr, n, ch = step
                     _lib.check(L.ojdf_avgpool3_batched(arr, n, H, W, ch, 1, st))

@@ -174,3 +174,42 @@ def test_fuse_training_values_vs_reference_golden(golden):
     assert np.array_equal(db.scenes_est['synth0'].volume.cpu().numpy().view(np.uint16), g['tsdf'])
     assert np.array_equal(db.fusion_weights['synth0'].cpu().numpy().view(np.uint16), g['wvol'])
     assert int(db.ids_est['synth0'].volume.count_nonzero()) == 0             # test=False: no semantic update
+
+
+def test_frame_stream_equals_synchronous_fuse():
+    """stream.FrameStream (pinned host frames, copies / read-backs overlapped with the kernels of the neighbouring frames)
+    leaves bit-identical volumes to calling Pipeline.fuse frame by frame, and returns every frame's result in order."""
+    from online_joint_depthfusion_and_semantic_b200.stream import FrameStream
+    h, w, G = 48, 64, 48
+    vols, results = [], []
+    for streamed in (False, True):
+        scene, cfg, pipe, db = _world(h, w, G, 'gt', False)
+        last = {}
+        inner = pipe._fusion
+
+        def tap(inputs, values, _inner=inner, _last=last, **kw):
+            est = _inner(inputs, values, **kw)
+            _last['v'] = est.abs().mean()
+            return est
+        pipe._fusion = tap
+        frames = [{k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in scene.frame(i, device='cpu').items()} for i in range(5)]
+        got = []
+        with torch.no_grad():
+            if streamed:
+                fs = FrameStream(pipe, db, DEV, result_fn=lambda: last['v'], depth=2)
+                for b in frames:
+                    r = fs.submit(b)
+                    if r is not None:
+                        got.append(r)
+                got += fs.flush()
+                assert fs.h2d_bytes > 0
+            else:
+                for b in frames:
+                    pipe.fuse({k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in b.items()}, db, DEV)
+                    got.append(float(last['v'].item()))
+        torch.cuda.synchronize()
+        v = db['s0']
+        vols.append([v['current'].cpu().numpy().view(np.uint16).copy(), v['weights'].cpu().numpy().view(np.uint16).copy()])
+        results.append(got)
+    assert len(results[1]) == 5 and results[0] == results[1]
+    assert np.array_equal(vols[0][0], vols[1][0]) and np.array_equal(vols[0][1], vols[1][1])
