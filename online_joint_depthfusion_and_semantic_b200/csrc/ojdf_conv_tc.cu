@@ -619,6 +619,11 @@ extern "C" int ojdf_conv_tc_batched(const ojdf_conv_problem *problems_host, int 
     {   // 3x3 layers whose halo box fits in shared memory go to the shared-memory-operand kernel (ojdf_conv_ss.cu), the
         // rest stays here.  OJDF_CONV_KERNEL=ts / flag 65536: always this file's kernel; =ss / flag 32768: always the other.
         static const int env = [] { const char *e = getenv("OJDF_CONV_KERNEL"); return !e ? 0 : !strcmp(e, "ts") ? 1 : !strcmp(e, "ss") ? 2 : 0; }();
+        if (!(flags & (65536 | 32768)) && env == 0) {             // small maps with wide outputs: channels as M, the image as N
+            const int r = ojdf_conv_wt_launch(problems_host, n_problems, cin, cout, H, W, taps, act, slope, out_mul, npad_req, flags,
+                                              scratch_dev, scratch_bytes, stream);
+            if (r != OJDF_SS_DECLINED) return r;
+        }
         if (!(flags & 65536) && env != 1) {
             const int r = ojdf_conv_ss_launch(problems_host, n_problems, cin, cout, H, W, taps, act, slope, out_mul, npad_req,
                                               flags | (env == 2 ? 32768 : 0), scratch_dev, scratch_bytes, stream);

@@ -303,15 +303,16 @@ int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, 
         prm.p[i] = tc::Problem{q.weights_dev, q.scale_dev, q.shift_dev, q.out_dev, q.residual_dev,
                                 q.out_stride, q.out_coffset, q.dilation, q.residual_stride};
     }
-    // split the K loop over CTAs: about four K steps (~1 us of MMAs each) per CTA, at most one CTA per SM
+    // split the K loop over CTAs: two K steps per CTA when the SMs allow it (both stage loads are in flight from the start:
+    // a CTA is bound by the ~2 us latency of a 110 KB stage, not by its ~1 us of MMAs), at most one CTA per SM
     const long long items = (long long)n_problems * groups;
     prm.ksplit = 1;
     prm.cpad = groups * 128;
     if (scratch_dev && !(flags & 4096)) {
-        int ks = min_steps / 4;
+        int ks = min_steps / 2;
         const int room = (int)(tc::sm_count() / items);
         if (ks > room) ks = room;
-        if (ks > 16) ks = 16;
+        if (ks > 32) ks = 32;
         const size_t per_split = (size_t)n_problems * npix * prm.cpad * sizeof(float);
         if ((size_t)ks * per_split > scratch_bytes) ks = (int)(scratch_bytes / per_split);
         if (ks >= 2) prm.ksplit = ks;

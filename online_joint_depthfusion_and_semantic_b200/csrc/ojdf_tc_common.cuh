@@ -242,3 +242,7 @@ void ojdf_tc_layout(int cout, int npad_req, int *npad, int *groups);
 #define OJDF_SS_DECLINED (-1000)
 int ojdf_conv_ss_launch(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W, int taps, int act,
                         float slope, float out_mul, int npad_req, int flags, float *scratch_dev, size_t scratch_bytes, void *stream);
+// ojdf_conv_wt.cu: output channels as the M dimension, the whole (small) image as N -- feature maps of <= 304 pixels
+// with >= 128 output channels (AdapNet++ at 15x20); OJDF_SS_DECLINED for everything else.
+int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W, int taps, int act,
+                        float slope, float out_mul, int npad_req, int flags, float *scratch_dev, size_t scratch_bytes, void *stream);
