@@ -40,6 +40,7 @@ __device__ __forceinline__ float activate(float v, int act, float slope)
 __global__ void __launch_bounds__(256)
 conv_reduce_kernel(ConvBatch batch, int npix, int cout, int cpad, int splits, int act, float slope, float out_mul)
 {
+    asm volatile("griddepcontrol.wait;" ::: "memory");         // launched behind the convolution programmatically: its partials are complete from here on
     const ConvProblem pr = batch.p[blockIdx.y];
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)npix * cout) return;
@@ -53,6 +54,53 @@ conv_reduce_kernel(ConvBatch batch, int npix, int cout, int cpad, int splits, in
     }
     if (pr.residual) v += pr.residual[(size_t)p * pr.res_stride + c];
     pr.out[(size_t)p * pr.out_stride + pr.out_coff + c] = activate(v, act, slope) * out_mul;
+}
+
+// The same with four channels per thread (128-bit loads; cout, cpad, the row strides and the channel offset multiples of 4)
+// and the slice loads of a thread issued eight at a time before they are summed (in slice order, like the scalar kernel).
+__global__ void __launch_bounds__(256)
+conv_reduce4_kernel(ConvBatch batch, int npix, int cout, int cpad, int splits, int act, float slope, float out_mul)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const ConvProblem pr = batch.p[blockIdx.y];
+    const int c4n = cout >> 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)npix * c4n) return;
+    const int p = (int)(i / c4n), c = (int)(i - (long long)p * c4n) * 4;
+    const float *src = pr.partial + (size_t)p * cpad + c;
+    const size_t slab = (size_t)npix * cpad;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    for (; s + 8 <= splits; s += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldcs(reinterpret_cast<const float4 *>(src + (size_t)(s + j) * slab));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+    }
+    if (s + 4 <= splits) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __ldcs(reinterpret_cast<const float4 *>(src + (size_t)(s + j) * slab));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+        s += 4;
+    }
+    for (; s < splits; ++s) {
+        const float4 v = __ldcs(reinterpret_cast<const float4 *>(src + (size_t)s * slab));
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(pr.scale + c)), sh = __ldg(reinterpret_cast<const float4 *>(pr.shift + c));
+    float v[4] = {fmaf(a.x, sc.x, sh.x), fmaf(a.y, sc.y, sh.y), fmaf(a.z, sc.z, sh.z), fmaf(a.w, sc.w, sh.w)};
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pr.residual) r = *reinterpret_cast<const float4 *>(pr.residual + (size_t)p * pr.res_stride + c);
+    const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (act == kSigmoidMul) v[j] = rr[j] / (1.0f + expf(-v[j])) * out_mul;
+        else v[j] = activate(pr.residual ? v[j] + rr[j] : v[j], act, slope) * out_mul;
+    }
+    *reinterpret_cast<float4 *>(pr.out + (size_t)p * pr.out_stride + pr.out_coff + c) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // 3x3 average pool, stride 1, zero padding counted in the divisor (nn.AvgPool2d default), NHWC.
@@ -413,8 +461,31 @@ int launch_split_reduce(const SplitReduce *problems, int n, int npix, int cout, 
         b.p[i] = ConvProblem{nullptr, nullptr, q.scale, q.shift, q.out, q.residual, q.partial, 0, q.out_stride, q.out_coff, 1,
                              q.res_stride};
     }
-    dim3 rgrid((unsigned)(((long long)npix * cout + 255) / 256), n);
-    conv_reduce_kernel<<<rgrid, 256, 0, s>>>(b, npix, cout, cpad, splits, act, slope, out_mul);
+    bool vec = !(cout & 3) && !(cpad & 3);
+    for (int i = 0; i < n && vec; ++i) {
+        const SplitReduce &q = problems[i];
+        vec = !(q.out_stride & 3) && !(q.out_coff & 3) && !((uintptr_t)q.out & 15) && !((uintptr_t)q.partial & 15) &&
+              !((uintptr_t)q.scale & 15) && !((uintptr_t)q.shift & 15) && (!q.residual || (!(q.res_stride & 3) && !((uintptr_t)q.residual & 15)));
+    }
+    // programmatic dependent launch: the reduction's blocks are scheduled while the convolution (which released its
+    // dependents at its first instruction) is still running and wait in griddepcontrol.wait for its completion
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t le;
+    if (vec) {
+        cfg.gridDim = dim3((unsigned)(((long long)npix * (cout >> 2) + 255) / 256), n);
+        le = cudaLaunchKernelEx(&cfg, conv_reduce4_kernel, b, npix, cout, cpad, splits, act, slope, out_mul);
+    } else {
+        cfg.gridDim = dim3((unsigned)(((long long)npix * cout + 255) / 256), n);
+        le = cudaLaunchKernelEx(&cfg, conv_reduce_kernel, b, npix, cout, cpad, splits, act, slope, out_mul);
+    }
+    if (le != cudaSuccess) { cudaGetLastError(); return (int)le; }
     return launched(1);
 }
 

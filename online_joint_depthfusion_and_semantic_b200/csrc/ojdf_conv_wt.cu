@@ -34,6 +34,7 @@ struct WtParams {
     CUtensorMap in_map[kMaxBatch];
     Problem p[kMaxBatch];
     int H, W, npix, npad_n, n1, n2, cin, cout, taps, act, groups, nkc, nprob, ksplit, cpad, stages, box_bytes, b_slot, fast;
+    int th, ntiles;                                            // pixel tile: th whole image rows (th * W <= 304), ntiles of them
     int ntaps[kMaxBatch];
     int tap_list[kMaxBatch][9];
     float slope, out_mul;
@@ -49,14 +50,16 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t adesc, ui
         : "memory");
 }
 
-struct Item { int z, g, s0, s1, ks; };
+struct Item { int z, g, s0, s1, ks, tile; };
 __device__ __forceinline__ Item decode(const WtParams &prm, int it)
 {
     Item i;
     i.ks = it % prm.ksplit;
-    const int zg = it / prm.ksplit;
-    i.g = zg % prm.groups;
-    i.z = zg / prm.groups;
+    int r = it / prm.ksplit;
+    i.tile = r % prm.ntiles;
+    r /= prm.ntiles;
+    i.g = r % prm.groups;
+    i.z = r / prm.groups;
     const int total = prm.ntaps[i.z] * prm.nkc;                 // K steps of this problem: live taps x 32-channel chunks
     i.s0 = total * i.ks / prm.ksplit;
     i.s1 = total * (i.ks + 1) / prm.ksplit;
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) conv_wt_kernel(const __grid_con
     auto lo_full = [&](int s) { return bar0 + 8u * (2 * kMaxStages + s); };
     const uint32_t acc_full = bar0 + 8u * (3 * kMaxStages), acc_empty = acc_full + 8u;
 
-    const int total = prm.nprob * prm.groups * prm.ksplit;
+    const int total = prm.nprob * prm.groups * prm.ntiles * prm.ksplit;
     const int begin = (int)((long long)total * blockIdx.x / gridDim.x);
     const int end = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
 
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) conv_wt_kernel(const __grid_con
                 if (elect_one()) {
                     const uint32_t dst = base + (uint32_t)r.idx * slot_bytes;
                     mbar_expect_tx(full(r.idx), (uint32_t)prm.box_bytes + kABytes);
-                    tma_load_3d(dst, &prm.in_map[I.z], full(r.idx), kc * kBK, dx, dy);
+                    tma_load_3d(dst, &prm.in_map[I.z], full(r.idx), kc * kBK, dx, I.tile * prm.th + dy);
                     bulk_load(dst + 2u * (uint32_t)prm.b_slot, wbase + (size_t)(tap * prm.nkc + kc) * kABytes, kABytes, full(r.idx));
                 }
                 __syncwarp();
@@ -210,28 +213,35 @@ __global__ void __launch_bounds__(kWtThreads, 1) conv_wt_kernel(const __grid_con
             mbar_wait(acc_full, acc_phase);
             tc_fence_after();
             acc_phase ^= 1u;
+            const int p0 = I.tile * prm.th * prm.W;             // first pixel of this tile
+            int pend = p0 + prm.th * prm.W;                       // one past its last real pixel
+            if (pend > prm.npix) pend = prm.npix;
             for (int n0 = half * 16; n0 < prm.npad_n; n0 += 32) {
                 uint32_t v[16];
                 tmem_ld16(lane_base + (uint32_t)n0, v);
                 tmem_ld_wait();
                 if (!live) continue;
                 if (prm.ksplit > 1) {                           // raw partial sums: [ks][pixel][cpad]
-                    float *o = pr.out + ((size_t)I.ks * prm.npix + n0) * prm.cpad + co;
+                    float *o = pr.out + ((size_t)I.ks * prm.npix + p0 + n0) * prm.cpad + co;
 #pragma unroll
                     for (int c = 0; c < 16; ++c)
-                        if (n0 + c < prm.npix) o[(size_t)c * prm.cpad] = __uint_as_float(v[c]);
+                        if (p0 + n0 + c < pend) o[(size_t)c * prm.cpad] = __uint_as_float(v[c]);
                 } else {
+                    // the residual values of the chunk are read first: loads interleaved with the stores below would be
+                    // serialised by the compiler (the output may alias them)
+                    float res[16];
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
-                        const int p = n0 + c;
-                        if (p >= prm.npix) continue;
+                        const int p = p0 + n0 + c;
+                        res[c] = (pr.residual && p < pend) ? __ldg(pr.residual + (size_t)p * pr.res_stride + co) : 0.0f;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const int p = p0 + n0 + c;
+                        if (p >= pend) continue;
                         float r = fmaf(__uint_as_float(v[c]), sc, sh);
-                        if (prm.act == kSigmoidMul) {
-                            r = pr.residual[(size_t)p * pr.res_stride + co] / (1.0f + expf(-r));
-                        } else {
-                            if (pr.residual) r += pr.residual[(size_t)p * pr.res_stride + co];
-                            r = activate(r, prm.act, prm.slope);
-                        }
+                        if (prm.act == kSigmoidMul) r = res[c] / (1.0f + expf(-r));
+                        else r = activate(r + res[c], prm.act, prm.slope);
                         pr.out[(size_t)p * pr.out_stride + pr.out_coff + co] = r * prm.out_mul;
                     }
                 }
@@ -250,8 +260,9 @@ __global__ void __launch_bounds__(kWtThreads, 1) conv_wt_kernel(const __grid_con
 
 using namespace ojdf;
 
-// Returns OJDF_SS_DECLINED (nothing launched) for shapes this kernel does not cover: more than 304 pixels, output-channel
-// groups narrower than 128, strided reads / writes.  flag 131072 forces the other kernels.
+// Returns OJDF_SS_DECLINED (nothing launched) for shapes this kernel does not cover: output-channel groups narrower than
+// 128, images wider than 256 pixels, strided writes.  Larger maps are cut into pixel tiles of whole image rows (<= 304
+// pixels each).  flag 131072 forces the other kernels, flag 262144 keeps maps of more than one pixel tile on them.
 int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, int cin, int cout, int H, int W, int taps, int act,
                         float slope, float out_mul, int npad_req, int flags, float *scratch_dev, size_t scratch_bytes, void *stream)
 {
@@ -260,9 +271,18 @@ int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, 
     int npad, groups;
     ojdf_tc_layout(cout, npad_req, &npad, &groups);
     const int npix = H * W;
-    if (npix > wt::kMaxPix || W > 256 || H > 256 || npad != 128) return OJDF_SS_DECLINED;
+    if (W > 256 || npad != 128) return OJDF_SS_DECLINED;
+    int th = wt::kMaxPix / W;                                   // image rows per pixel tile
+    if (th > H) th = H;
+    if (th > 256) th = 256;
+    if (th < 1) return OJDF_SS_DECLINED;
+    const int ntiles = (H + th - 1) / th;
+    // wide maps: the pixel-major kernels share a weight stage between several pixel tiles, this one re-reads it per tile --
+    // it wins while the whole layer is a handful of K steps per CTA (measured on B200, tools/tc_probe.py)
+    if (ntiles > 1 && (flags & 262144)) return OJDF_SS_DECLINED;
     for (int i = 0; i < n_problems; ++i)
-        if (problems_host[i].in_step > 1 || problems_host[i].out_step > 1) return OJDF_SS_DECLINED;
+        if (problems_host[i].out_step > 1 || (problems_host[i].in_step > 1 && (problems_host[i].in_step != 2 || problems_host[i].in_width < (W - 1) * 2 + 1)))
+            return OJDF_SS_DECLINED;
     wt::WtParams prm;
     memset(&prm, 0, sizeof(prm));
     prm.H = H; prm.W = W; prm.npix = npix; prm.cin = cin; prm.cout = cout; prm.taps = taps; prm.act = act;
@@ -270,10 +290,11 @@ int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, 
     prm.nkc = (cin + tc::kBK - 1) / tc::kBK;
     prm.slope = slope; prm.out_mul = out_mul;
     prm.fast = (flags & 64) ? 1 : 0;
-    prm.npad_n = (npix + 15) & ~15;
+    prm.th = th; prm.ntiles = ntiles;
+    prm.npad_n = (th * W + 15) & ~15;
     if (prm.npad_n <= 256) { prm.n1 = prm.npad_n; prm.n2 = 0; }
     else { prm.n1 = ((prm.npad_n / 2) + 15) & ~15; prm.n2 = prm.npad_n - prm.n1; }
-    prm.box_bytes = npix * 128;
+    prm.box_bytes = th * W * 128;
     prm.b_slot = (prm.npad_n * 128 + 1023) / 1024 * 1024;       // the MMAs read npad_n rows: the tail rows are never stored
     const int slot = 2 * prm.b_slot + (int)wt::kABytes;
     const int budget = 227 * 1024 - 1024 - 1024;
@@ -287,7 +308,9 @@ int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, 
             ((uintptr_t)q.in_dev & 15) || ((uintptr_t)q.weights_dev & 15) || q.out_stride < q.out_coffset + cout ||
             q.out_coffset < 0 || q.dilation < 1 || (q.residual_dev && q.residual_stride < cout) || (act == 5 && !q.residual_dev))
             return OJDF_ERR_BADARG;
-        const int r = tc::pixel_map(q.in_dev, cin, q.in_stride, H, W, W, H, &prm.in_map[i]);
+        const int step = q.in_step > 1 ? q.in_step : 1;          // stride-2 reads live in the tensor map
+        const int r = tc::pixel_map(q.in_dev, cin, q.in_stride * step, H, W, W, th, &prm.in_map[i],
+                                    step > 1 ? (long long)q.in_stride * q.in_width * step : 0);
         if (r) return r;
         int mask = taps == 9 ? (q.tap_mask ? (q.tap_mask & 511) : 511) : 1;
         if (taps == 9) {                                         // taps that only ever see the zero padding
@@ -305,7 +328,7 @@ int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, 
     }
     // split the K loop over CTAs: two K steps per CTA when the SMs allow it (both stage loads are in flight from the start:
     // a CTA is bound by the ~2 us latency of a 110 KB stage, not by its ~1 us of MMAs), at most one CTA per SM
-    const long long items = (long long)n_problems * groups;
+    const long long items = (long long)n_problems * groups * ntiles;
     prm.ksplit = 1;
     prm.cpad = groups * 128;
     if (scratch_dev && !(flags & 4096)) {
@@ -317,6 +340,9 @@ int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, 
         if ((size_t)ks * per_split > scratch_bytes) ks = (int)(scratch_bytes / per_split);
         if (ks >= 2) prm.ksplit = ks;
     }
+    // long 1x1 K loops over many pixel tiles: the pixel-major kernel shares each weight stage between pixel tiles and wins
+    // (measured: 60x80, 256 -> 256: 20 us there, 32 us here)
+    if (ntiles > 1 && taps == 1 && min_steps / prm.ksplit > 6) return OJDF_SS_DECLINED;
     tc::SplitReduce red[tc::kMaxBatch];
     if (prm.ksplit > 1)
         for (int i = 0; i < n_problems; ++i) {

@@ -41,6 +41,11 @@ CASES = [
     ('A: 3x3 60x80 64->64 x2 (layer1)', 60, 80, 64, 64, 9, 1, 64, 64, 0, 1, False, 2, 0),
     ('A: 1x1 60x80 64->256 x2 residual', 60, 80, 64, 256, 1, 1, 64, 256, 0, 1, True, 2, 0),
     ('A: 3x3 30x40 48->4 relu (SSMA)', 30, 40, 48, 4, 9, 1, 48, 4, 0, 1, False, 1, 1),
+    ('A: 1x1 30x40 128->512 x2 residual', 30, 40, 128, 512, 1, 1, 128, 512, 0, 1, True, 2, 0),
+    ('A: 1x1 30x40 512->128 x2', 30, 40, 512, 128, 1, 1, 512, 128, 0, 1, False, 2, 0),
+    ('A: 3x3 30x40 280->256 (decoder stage 2)', 30, 40, 280, 256, 9, 1, 280, 256, 0, 1, False, 1, 0),
+    ('A: 3x3 30x40 256->128 x4 (layer3[0] conv2a/b)', 30, 40, 256, 128, 9, 2, 256, 256, 0, 1, False, 4, 0),
+    ('A: 1x1 60x80 256->256 x2 (wide 1x1 at 60x80)', 60, 80, 256, 256, 1, 1, 256, 256, 0, 1, False, 2, 0),
     # role profile / timing experiments (flag 128 = per-role wait cycles of block 0; 16 = no MMAs, 32 = no split
     # work, 64 = 1xTF32, 1024 = busy-poll the A ring, 2048 = single accumulator set)
     ('P: dense', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 128 | 1),
