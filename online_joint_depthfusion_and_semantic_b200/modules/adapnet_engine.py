@@ -253,6 +253,7 @@ class AdapNetEngine:
         self.dims = (H4, W4, H8, W8, H16, W16)
         self._keep, self.plan = [], []
         self._join_w = {}
+        self.side = None
         plan = self.plan
 
         def z(npix, c):
@@ -356,6 +357,7 @@ class AdapNetEngine:
         self.SK1 = z(N8, n * 24)
         sk1 = [mk(e.enc_skip1_conv, e.enc_skip1_conv_bn, 'none', H8, W8) for e in encs]
         conv_step([(sk1[e], sk1[e].problem(cur[e], cs, self.SK1, n * 24, e * 24)) for e in range(n)], H8, W8)
+        self._after_skips = len(plan)                            # both skip tensors exist from here on
         ms = [e.res_n50_enc.layer3[0] for e in encs]
         unit(ms, cur, cs, H8, W8, [self.tail.X[e][0] for e in range(n)], self.tail.cmax)
         plan.append(('tail',))
@@ -400,9 +402,16 @@ class AdapNetEngine:
             self._join_w[id(conv)] = (conv.weight.detach().reshape(24, 256).float().contiguous().to(dev),
                                       conv.bias.detach().float().contiguous().to(dev))
         if self.stage2:
+            # the two skip SSMAs (six small launches of 10..40 CTAs) only need the skip tensors: they run on a side stream
+            # next to layer3 / layer4 / eASPP (whose grids leave SMs free) and join before the decoder reads them
+            mark = len(plan)
             self.skip2 = ssma(net.ssma_s2, self.SK2, N4, H4, W4, 24)
             self.skip1 = ssma(net.ssma_s1, self.SK1, N8, H8, W8, 24)
+            side_block = [('side_begin',)] + plan[mark:] + [('side_end',)]
+            del plan[mark:]
+            plan[self._after_skips:self._after_skips] = side_block
             self.X16 = ssma(net.ssma_res, self.FX, N16, H16, W16, 256)
+            plan.append(('join_side',))
         else:
             self.skip2, self.skip1, self.X16 = self.SK2, self.SK1, self.FX
         # ---- decoder: transposed convolutions / aux heads stay on the library, on channels-last views
@@ -444,12 +453,27 @@ class AdapNetEngine:
             arr = (StemProblem * self.n)(*[StemProblem(xs[e].data_ptr(), self.stem[e][0].data_ptr(), self.stem[e][1].data_ptr(),
                                                        self.stem[e][2].data_ptr(), self.S0[e].data_ptr(), 64, 0) for e in range(self.n)])
             _lib.check(L.ojdf_adapnet_stem(arr, self.n, self.h, self.w, st))
+            main = torch.cuda.current_stream(dev)
+            on_side = False
             for step in self.plan:
                 kind = step[0]
                 if kind == 'conv':
                     _, arr, n, cin, cout, H, W, taps, act, slope, npad_req = step
-                    _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 1 | self.flags,
-                                                      self.tail.scratch.data_ptr(), self.tail.scratch.numel() * 4, st))
+                    if on_side:                                  # no split-K scratch on the side stream: it belongs to the main one
+                        _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 1 | self.flags,
+                                                          None, 0, self.side.cuda_stream))
+                    else:
+                        _lib.check(L.ojdf_conv_tc_batched(arr, n, cin, cout, H, W, taps, act, slope, 1.0, npad_req, 1 | self.flags,
+                                                          self.tail.scratch.data_ptr(), self.tail.scratch.numel() * 4, st))
+                elif kind == 'side_begin':
+                    if self.side is None:
+                        self.side = torch.cuda.Stream(device=dev)
+                    self.side.wait_stream(main)
+                    on_side = True
+                elif kind == 'side_end':
+                    on_side = False
+                elif kind == 'join_side':
+                    main.wait_stream(self.side)
                 elif kind == 'tail':
                     self.tail.run(st)
                 elif kind == 'dropout':
