@@ -50,7 +50,14 @@ from online_joint_depthfusion_and_semantic_b200.synthetic import SyntheticScene 
 H, W, GRID, N_CLASSES = 240, 320, 256, 30
 # dram__bytes_read.sum + dram__bytes_write.sum per frame of each stage's kernels, from the committed `ncu --set full`
 # capture of this very command (profiles/r2_*; filled in after each kernel change, None = not captured for this build)
-TRAFFIC = {'fusionnet': None, 'integrate': None, 'extract': None}
+TRAFFIC = {'fusionnet': None, 'integrate': None, 'extract': None, 'adapnet': None}
+_TRAFFIC_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r2_traffic.json')
+if os.path.exists(_TRAFFIC_FILE):                      # written by profiles/make_traffic.py from the committed launch list
+    try:
+        _t = json.load(open(_TRAFFIC_FILE))
+        TRAFFIC = {k: (_t[k]['dram_bytes_per_frame'] if k in _t else None) for k in TRAFFIC}
+    except (ValueError, KeyError, TypeError):
+        pass
 SCENES_PER_RANK, FRAMES_PER_SCENE = 4, 6
 METRIC = 'fused_frames_per_second_240x320_into_256cube'
 WORKLOAD = 'configs[1]: synthetic Replica-like room, 256^3 grid, 240x320 RGB-D, AdapNet++(stage2,30cls)+FusionNet_v3(sem)+extract+integrate'
@@ -325,17 +332,26 @@ def run_own(args):
     roof_ext = {'kernel': 'ojdf_rays + ojdf_gather (extract_kernel: per-ray records, then the fused gather that also writes '
                           'FusionNet\'s input rows)', 'bound': 'hbm',
                 'achieved': ext_bytes / (ext_total * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
-                'frac': ext_bytes / (ext_total * 1e-3) / 1e9 / peak, 'traffic': TRAFFIC.get('extract'), 'peak_source': peak_src,
+                'frac': ext_bytes / (ext_total * 1e-3) / 1e9 / peak, 'traffic': TRAFFIC.get('extract') if PRECISION == 'parity' else None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': ext_bytes, 'ms_per_launch': float(ext_total)}
     fn_flop = 78.15e9 * (H * W) / 76800.0            # FusionNet_v3 (semantic head on), convolutions only, 2*MAC
     fn_ms = stages['fusionnet']
-    roof_conv = {'kernel': 'tc::conv_tc_kernel (tcgen05 kind::tf32 tap GEMM, 3xTF32 split precision) over the FusionNet_v3 stack: '
-                           '33 launches per frame + 13 small pooling / bias / packing launches inside the same bracket',
+    roof_conv = {'kernel': 'the tcgen05 kind::tf32 convolution kernels (3xTF32 split precision) over the FusionNet_v3 stack: ss::conv_ss_kernel '
+                           '(dense blocks), tc::conv_tc_kernel (vortex 1x1 / dilated 3x3), chain::conv_chain_kernel (vortex tails, Pred stack): '
+                           '21 launches per frame + 12 small pooling / bias launches inside the same bracket',
                  'bound': 'tensor', 'achieved': fn_flop / (fn_ms * 1e-3) / 1e12, 'peak': tpeak, 'unit': 'TFLOP/s',
-                 'frac': fn_flop / (fn_ms * 1e-3) / 1e12 / tpeak, 'traffic': TRAFFIC.get('fusionnet'),
+                 'frac': fn_flop / (fn_ms * 1e-3) / 1e12 / tpeak, 'traffic': TRAFFIC.get('fusionnet') if PRECISION == 'parity' else None,
                  'peak_source': peak_src + ', dense bf16 sustained; the kernel issues 3 tf32 MMAs per algorithmic MAC '
                                            '(tf32 dense peak is half of bf16), so 1/6 of this peak is its arithmetic ceiling',
                  'algorithmic_flop_per_frame': fn_flop, 'ms_per_frame': float(fn_ms)} if fn_ms else None
+    an_flop = 59.1e9 * (H * W) / 76800.0             # AdapNet++ stage 2 (both encoders, eASPP, SSMA, decoder), convolutions only, 2*MAC
+    an_ms = stages['adapnet']
+    roof_adap = {'kernel': 'the same kernels + wt::conv_wt_kernel (small maps: output channels as M, the image as N) over AdapNet++ stage 2, '
+                           'replayed as one CUDA graph (stem, softmax / arg-max and split-K reductions inside the same bracket)',
+                 'bound': 'tensor', 'achieved': an_flop / (an_ms * 1e-3) / 1e12, 'peak': tpeak, 'unit': 'TFLOP/s',
+                 'frac': an_flop / (an_ms * 1e-3) / 1e12 / tpeak, 'traffic': TRAFFIC.get('adapnet') if PRECISION == 'parity' else None,
+                 'peak_source': peak_src + ', dense bf16 sustained (1/6 of it is the 3xTF32 arithmetic ceiling)',
+                 'algorithmic_flop_per_frame': an_flop, 'ms_per_frame': float(an_ms)} if an_ms else None
     line = {
         'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -352,7 +368,7 @@ def run_own(args):
                 'value_synchronous': world * args.steps / (ms_e2e_sync / 1e3),
                 'synchronous_call': 'Pipeline.fuse(host batch) + .item() of the result every step (no overlap between frames)'},
         'gpu_launches': int(launches), 'clocks': clocks,
-        'roofline': roof_conv, 'roofline_integrate': roof_int, 'roofline_extract': roof_ext,
+        'roofline': roof_conv, 'roofline_adapnet': roof_adap, 'roofline_integrate': roof_int, 'roofline_extract': roof_ext,
         'stage_ms': stages,
     }
     if world == 1 and not args.no_cpu_baseline:
