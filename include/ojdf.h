@@ -266,6 +266,8 @@ typedef struct ojdf_pool_problem {
     const float *scale_dev;
     const float *shift_dev;
     int in_stride, out_stride;
+    int identity;                   /* 1: no pooling, only the scale / shift (/ ReLU) epilogue (VortexPooling's branch 0, whose 1x1
+                                     * product comes out of the same merged launch as the pooled branches') */
 } ojdf_pool_problem;
 int ojdf_avgpool3_batched(const ojdf_pool_problem *problems_host, int n_problems, int H, int W, int C, int relu, void *stream);
 /* VortexPooling global branch (modules/model.py:107-112) folded into the bias of the `final` 1x1 conv:

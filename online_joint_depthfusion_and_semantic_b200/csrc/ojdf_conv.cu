@@ -133,6 +133,7 @@ avgpool3_kernel(const float *__restrict__ in, int in_stride, int H, int W, int C
 struct PoolProblem {
     const float *in; float *out; const float *scale; const float *shift;      // scale == nullptr: plain pool
     int in_stride, out_stride;
+    int identity;                                                             // 1: no pooling, only the scale / shift / ReLU epilogue
 };
 struct PoolBatch { PoolProblem p[kMaxBatch]; };
 
@@ -146,16 +147,21 @@ avgpool3_batched_kernel(PoolBatch batch, int H, int W, int C, int relu)
     const int c4 = (int)(i % c4n);
     const int p = (int)(i / c4n), y = p / W, x = p - y * W;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 o;
+    if (pr.identity) {
+        o = __ldg(reinterpret_cast<const float4 *>(pr.in + (size_t)p * pr.in_stride) + c4);
+    } else {
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy)
+        for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int yy = y + dy, xx = x + dx;
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(pr.in + (size_t)(yy * W + xx) * pr.in_stride) + c4);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
-    float4 o = make_float4(s.x / 9.0f, s.y / 9.0f, s.z / 9.0f, s.w / 9.0f);
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int yy = y + dy, xx = x + dx;
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(pr.in + (size_t)(yy * W + xx) * pr.in_stride) + c4);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+        o = make_float4(s.x / 9.0f, s.y / 9.0f, s.z / 9.0f, s.w / 9.0f);
+    }
     if (pr.scale) {
         const float4 a = __ldg(reinterpret_cast<const float4 *>(pr.scale) + c4), b = __ldg(reinterpret_cast<const float4 *>(pr.shift) + c4);
         o.x = fmaf(o.x, a.x, b.x); o.y = fmaf(o.y, a.y, b.y); o.z = fmaf(o.z, a.z, b.z); o.w = fmaf(o.w, a.w, b.w);
@@ -515,7 +521,7 @@ extern "C" int ojdf_avgpool3_batched(const ojdf_pool_problem *problems_host, int
                                q.out_stride < C || (q.scale_dev && !q.shift_dev) || ((uintptr_t)q.in_dev & 15) ||
                                ((uintptr_t)q.out_dev & 15) || ((uintptr_t)q.scale_dev & 15) || ((uintptr_t)q.shift_dev & 15)))
             return OJDF_ERR_BADARG;
-        b.p[i] = PoolProblem{q.in_dev, q.out_dev, q.scale_dev, q.shift_dev, q.in_stride, q.out_stride};
+        b.p[i] = PoolProblem{q.in_dev, q.out_dev, q.scale_dev, q.shift_dev, q.in_stride, q.out_stride, q.identity ? 1 : 0};
     }
     const long long n = (long long)H * W * (C >> 2);
     avgpool3_batched_kernel<<<dim3((unsigned)((n + 255) / 256), n_problems), 256, 0, (cudaStream_t)stream>>>(b, H, W, C, relu);

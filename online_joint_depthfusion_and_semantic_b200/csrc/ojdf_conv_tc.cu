@@ -190,6 +190,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tc_fence_after();
             const int mask = prm.tap_mask[gr.z], tap0 = __ffs(mask) - 1;
             for (int kc = gr.kc0; kc < gr.kc1; ++kc) {
+                int ksteps = (prm.cin - kc * kBK + 7) >> 3;      // K steps of 8 channels that hold real channels
+                if (ksteps > kBK / 8) ksteps = kBK / 8;
                 for (int tap = 0; tap < prm.taps; ++tap) {
                     if (!((mask >> tap) & 1)) continue;
                     const int bs = rb.idx;
@@ -209,10 +211,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                 if (prm.dbg & 64) {                          // timing experiment: 1xTF32
 #pragma unroll
                                     for (int k = 0; k < kBK / 8; ++k)
-                                        umma_tf32_ts(acc, a_hi + k * 8, b_hi + (uint64_t)(k * 2), idesc, first | (uint32_t)k);
+                                        if (k < ksteps) umma_tf32_ts(acc, a_hi + k * 8, b_hi + (uint64_t)(k * 2), idesc, first | (uint32_t)k);
                                 } else {
 #pragma unroll
                                     for (int k = 0; k < kBK / 8; ++k) {
+                                        if (k >= ksteps) break;
                                         const uint64_t ko = (uint64_t)(k * 2);   // +32 bytes along K inside the swizzle atom
                                         umma_tf32_ts(acc, a_lo + k * 8, b_hi + ko, idesc, first | (uint32_t)k);
                                         umma_tf32_ts(acc, a_hi + k * 8, b_lo + ko, idesc, 1);
@@ -244,6 +247,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int dil = prm.p[gr.z].dil;
             const int mask = prm.tap_mask[gr.z];
             for (int kc = gr.kc0; kc < gr.kc1; ++kc) {
+                // a chunk with <= 24 real channels (the 19-channel layers, the tail of a 114-channel input) is split and
+                // stored as 24 columns: the splitter warps are the bottleneck of this kernel
+                const bool narrow = prm.cin - kc * kBK <= 24;
                 for (int box = 0; box < nbox; ++box) {
                     if (!halo_mode && !((mask >> box) & 1)) continue;
                     const int slot = rs.idx;
@@ -262,23 +268,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                             }
                             const int r = (mt * kBH + ty + oy) * prm.bwid + tx + ox;
                             const uint4 *row = reinterpret_cast<const uint4 *>(src + (size_t)r * 128);
-                            uint32_t hi[32], lo[32];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const uint4 x = row[j ^ (r & 7)];
-                                const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const uint32_t h = xs[e] & 0xFFFFE000u;
-                                    hi[4 * j + e] = h;
-                                    lo[4 * j + e] = __float_as_uint(__uint_as_float(xs[e]) - __uint_as_float(h));
-                                }
-                            }
-                            mbar_wait_p(a_empty(as), ra.phase ^ 1, 8 + 3 * set, prof, hot_hint);
-                            tc_fence_after();
                             const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(prm.acol0 + as * 64);
-                            tmem_st32(ta, hi);
-                            tmem_st32(ta + 32, lo);
+                            if (narrow) {
+                                uint32_t hi[24], lo[24];
+#pragma unroll
+                                for (int j = 0; j < 6; ++j) {
+                                    const uint4 x = row[j ^ (r & 7)];
+                                    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const uint32_t h = xs[e] & 0xFFFFE000u;
+                                        hi[4 * j + e] = h;
+                                        lo[4 * j + e] = __float_as_uint(__uint_as_float(xs[e]) - __uint_as_float(h));
+                                    }
+                                }
+                                mbar_wait_p(a_empty(as), ra.phase ^ 1, 8 + 3 * set, prof, hot_hint);
+                                tc_fence_after();
+                                tmem_st16(ta, hi);
+                                tmem_st8(ta + 16, hi + 16);
+                                tmem_st16(ta + 32, lo);
+                                tmem_st8(ta + 48, lo + 16);
+                            } else {
+                                uint32_t hi[32], lo[32];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const uint4 x = row[j ^ (r & 7)];
+                                    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const uint32_t h = xs[e] & 0xFFFFE000u;
+                                        hi[4 * j + e] = h;
+                                        lo[4 * j + e] = __float_as_uint(__uint_as_float(xs[e]) - __uint_as_float(h));
+                                    }
+                                }
+                                mbar_wait_p(a_empty(as), ra.phase ^ 1, 8 + 3 * set, prof, hot_hint);
+                                tc_fence_after();
+                                tmem_st32(ta, hi);
+                                tmem_st32(ta + 32, lo);
+                            }
                             tmem_st_wait();
                             tc_fence_before();
                             mbar_arrive(a_full(as));

@@ -81,7 +81,7 @@ def _ptrs(tensors):
 class PoolProblem(C.Structure):
     """include/ojdf.h: ojdf_pool_problem."""
     _fields_ = [('in_dev', C.c_void_p), ('out_dev', C.c_void_p), ('scale_dev', C.c_void_p), ('shift_dev', C.c_void_p),
-                ('in_stride', C.c_int), ('out_stride', C.c_int)]
+                ('in_stride', C.c_int), ('out_stride', C.c_int), ('identity', C.c_int)]
 
 
 class _Conv:
@@ -134,9 +134,17 @@ class _Vortex:
                           _Conv(br[6], br[7], 'relu', device), _Conv(br[9], br[10], 'relu', device)] for br in m.branches]
         # branches 1..3 see pool^b(x); their first 1x1 conv commutes with the pools, so it runs on x itself without
         # bias / BatchNorm / ReLU (`raw`), and those are applied after the last pool (scale / shift below, padded to 4)
-        self.raw = [None] + [_Conv(br[0], None, 'none', device, cin_map=in_map, raw=True) for br in list(m.branches)[1:]]
-        self.post = [None]
-        for b in range(1, 4):
+        # all four first-layer products in ONE convolution: 4 groups of (19 -> 20) output rows, bias / BatchNorm / ReLU later
+        mid = m.branches[0][0].out_channels
+        Gm = _pad4(mid)
+        merged = nn.Conv2d(m.branches[0][0].in_channels, 4 * Gm, 1, bias=False)
+        with torch.no_grad():
+            merged.weight.zero_()
+            for b, br in enumerate(m.branches):
+                merged.weight[b * Gm:b * Gm + mid] = br[0].weight.detach().cpu()
+        self.raw_all = _Conv(merged, None, 'none', device, cin_map=in_map, raw=True)
+        self.post = []
+        for b in range(0, 4):
             f = self.branches[b][0]
             sc, sh = torch.zeros(_pad4(f.cout), device=device), torch.zeros(_pad4(f.cout), device=device)
             sc[:f.cout], sh[:f.cout] = f.scale, f.shift
@@ -229,30 +237,41 @@ class FusionNetEngine:
             cin, Cv = vs[0].cin, vs[0].cout
             ps, Cvp = _pad4(cin), _pad4(Cv)
             tb = [[[z(mid_s) for _ in range(2)] for _ in range(4)] for _ in range(n)]
-            Y = [[None] + [z(mid_s) for _ in range(3)] for _ in range(n)]          # W_b . x, b = 1..3
             P1 = [[None, None] + [z(mid_s) for _ in range(2)] for _ in range(n)]   # pool(Y_b), b = 2, 3
             P2 = [z(mid_s) for _ in range(n)]                                       # pool(pool(Y_3))
             chained = self.chain and n <= 2 and Cv <= 128
             br_out = [None if chained else z(4 * Cvp) for _ in range(n)]   # the chain launch never materialises the branch outputs
-            self._keep += [tb, Y, P1, P2, br_out]
+            self._keep += [tb, P1, P2, br_out]
             # global-pool branch -> bias of the final conv: a long, thin reduction (two launches, one of them a single
             # block) that only the LAST conv of the vortex needs: it runs on a side stream next to the branch convolutions
             self.plan.append(('fork_bias',))
             for i, v in enumerate(vs):
                 self.plan.append(('bias', v, srcs[i], src_stride))
-            # branch 0: 1x1 + BN + ReLU on x; branches 1..3: the bare 1x1 product on x, then the cascaded pools
-            conv_step([(vs[i].branches[0][0], vs[i].branches[0][0].problem(srcs[i], src_stride, tb[i][0][0], mid_s)) for i in range(n)])
-            conv_step([(vs[i].raw[b], vs[i].raw[b].problem(srcs[i], src_stride, Y[i][b], mid_s)) for i in range(n) for b in (1, 2, 3)])
+            # the first 1x1 convolution of all four branches as ONE launch (the bare products W_b . x, 4 groups of 20 output
+            # channels: the activation operand is split once instead of four times); branch 0 gets its bias / BatchNorm /
+            # ReLU from an identity "pool", branches 1..3 after their cascaded pools
+            Yall = [z(4 * mid_s) for _ in range(n)]
+            self._keep.append(Yall)
+            conv_step([(vs[i].raw_all, vs[i].raw_all.problem(srcs[i], src_stride, Yall[i], 4 * mid_s)) for i in range(n)])
 
             def pool_step(items):
-                """items: (src, dst, (scale, shift) or None); one launch, ReLU where an epilogue is given."""
-                arr = (PoolProblem * len(items))(*[PoolProblem(a.data_ptr(), d.data_ptr(), e[0].data_ptr() if e else None,
-                                                               e[1].data_ptr() if e else None, mid_s, mid_s) for a, d, e in items])
-                self._keep.append([e for _, _, e in items])
+                """items: (src, dst, (scale, shift) or None[, identity]) with src = tensor or (tensor, channel offset, stride);
+                one launch, ReLU where an epilogue is given."""
+                probs = []
+                for it in items:
+                    a, d, e = it[:3]
+                    ident = int(it[3]) if len(it) > 3 else 0
+                    ptr, stride = (a[0].data_ptr() + 4 * a[1], a[2]) if isinstance(a, tuple) else (a.data_ptr(), mid_s)
+                    probs.append(PoolProblem(ptr, d.data_ptr(), e[0].data_ptr() if e else None, e[1].data_ptr() if e else None,
+                                             stride, mid_s, ident))
+                arr = (PoolProblem * len(items))(*probs)
+                self._keep.append([it[2] for it in items])
                 self.plan.append(('pools', arr, len(items), mid_s))
 
-            pool_step([(Y[i][1], tb[i][1][0], vs[i].post[1]) for i in range(n)] +
-                      [(Y[i][b], P1[i][b], None) for i in range(n) for b in (2, 3)])
+            ysl = lambda i, b: (Yall[i], b * mid_s, 4 * mid_s)   # noqa: E731  (branch b's product inside the merged buffer)
+            pool_step([(ysl(i, 0), tb[i][0][0], vs[i].post[0], 1) for i in range(n)] +
+                      [(ysl(i, 1), tb[i][1][0], vs[i].post[1]) for i in range(n)] +
+                      [(ysl(i, b), P1[i][b], None) for i in range(n) for b in (2, 3)])
             pool_step([(P1[i][2], tb[i][2][0], vs[i].post[2]) for i in range(n)] + [(P1[i][3], P2[i], None) for i in range(n)])
             pool_step([(P2[i], tb[i][3][0], vs[i].post[3]) for i in range(n)])
             conv_step([(vs[i].branches[b][1], vs[i].branches[b][1].problem(tb[i][b][0], mid_s, tb[i][b][1], mid_s))
