@@ -28,13 +28,13 @@ constexpr int kWtThreads = 32 * 18;
 constexpr int kEpiWarp0 = 2, kLoWarp0 = 10, kLoThreads = 256;
 constexpr int kMaxStages = 4;
 constexpr int kMaxPix = 304;
-constexpr uint32_t kABytes = 2 * 128 * 128;                   // [W_hi | W_lo] of 128 output channels x 32 input channels
 
 struct WtParams {
     CUtensorMap in_map[kMaxBatch];
     Problem p[kMaxBatch];
     int H, W, npix, npad_n, n1, n2, cin, cout, taps, act, groups, nkc, nprob, ksplit, cpad, stages, box_bytes, b_slot, fast;
     int th, ntiles;                                            // pixel tile: th whole image rows (th * W <= 304), ntiles of them
+    int npad, a_bytes;                                         // output channels per CTA (64 or 128) and bytes of its [W_hi | W_lo] stage
     int ntaps[kMaxBatch];
     int tap_list[kMaxBatch][9];
     float slope, out_mul;
@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) conv_wt_kernel(const __grid_con
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (base - raw);
     const int NS = prm.stages;
+    const uint32_t kABytes = (uint32_t)prm.a_bytes;              // [W_hi | W_lo] of npad output channels x 32 input channels
     const uint32_t slot_bytes = 2u * (uint32_t)prm.b_slot + kABytes;        // [box | lo copy | weights]
     const uint32_t bar0 = smem_u32(s_bars);
     auto full = [&](int s) { return bar0 + 8u * s; };
@@ -206,8 +207,8 @@ __global__ void __launch_bounds__(kWtThreads, 1) conv_wt_kernel(const __grid_con
         for (int it = begin; it < end; ++it) {
             const Item I = decode(prm, it);
             const Problem &pr = prm.p[I.z];
-            const int co = I.g * 128 + q * 32 + lane;
-            const bool live = co < prm.cout;
+            const int co = I.g * prm.npad + q * 32 + lane;
+            const bool live = q * 32 + lane < prm.npad && co < prm.cout;   // narrow groups: the MMA's upper rows read past W and are dropped
             float sc = 1.0f, sh = 0.0f;
             if (prm.ksplit == 1 && live) { sc = __ldg(pr.scale + co); sh = __ldg(pr.shift + co); }
             mbar_wait(acc_full, acc_phase);
@@ -271,7 +272,9 @@ int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, 
     int npad, groups;
     ojdf_tc_layout(cout, npad_req, &npad, &groups);
     const int npix = H * W;
-    if (W > 256 || npad != 128) return OJDF_SS_DECLINED;
+    // 64-channel groups run as M = 128 MMAs whose upper 64 rows read whatever follows the weight image (finite or not: a row of
+    // D depends on its own row of A only) and are never stored
+    if (W > 256 || (npad != 128 && npad != 64)) return OJDF_SS_DECLINED;
     int th = wt::kMaxPix / W;                                   // image rows per pixel tile
     if (th > H) th = H;
     if (th > 256) th = 256;
@@ -296,8 +299,11 @@ int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, 
     else { prm.n1 = ((prm.npad_n / 2) + 15) & ~15; prm.n2 = prm.npad_n - prm.n1; }
     prm.box_bytes = th * W * 128;
     prm.b_slot = (prm.npad_n * 128 + 1023) / 1024 * 1024;       // the MMAs read npad_n rows: the tail rows are never stored
-    const int slot = 2 * prm.b_slot + (int)wt::kABytes;
-    const int budget = 227 * 1024 - 1024 - 1024;
+    prm.npad = npad;
+    prm.a_bytes = 2 * npad * 128;
+    const int slot = 2 * prm.b_slot + prm.a_bytes;
+    const int tail_pad = (128 - npad) * 128;                    // what the last stage's W_lo descriptor reads past the stage
+    const int budget = 227 * 1024 - 1024 - 1024 - tail_pad;
     prm.stages = budget / slot;
     if (prm.stages > wt::kMaxStages) prm.stages = wt::kMaxStages;
     if (prm.stages < 2) return OJDF_SS_DECLINED;
@@ -330,7 +336,7 @@ int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, 
     // a CTA is bound by the ~2 us latency of a 110 KB stage, not by its ~1 us of MMAs), at most one CTA per SM
     const long long items = (long long)n_problems * groups * ntiles;
     prm.ksplit = 1;
-    prm.cpad = groups * 128;
+    prm.cpad = groups * npad;
     if (scratch_dev && !(flags & 4096)) {
         int ks = min_steps / 2;
         const int room = (int)(tc::sm_count() / items);
@@ -351,7 +357,7 @@ int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, 
             red[i] = tc::SplitReduce{q.scale_dev, q.shift_dev, q.residual_dev, q.out_dev, part, q.out_stride, q.out_coffset, q.residual_stride};
             prm.p[i].out = part;
         }
-    const size_t smem = (size_t)prm.stages * slot + 1024;
+    const size_t smem = (size_t)prm.stages * slot + 1024 + tail_pad;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(wt::conv_wt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
