@@ -35,6 +35,7 @@ struct WtParams {
     int H, W, npix, npad_n, n1, n2, cin, cout, taps, act, groups, nkc, nprob, ksplit, cpad, stages, box_bytes, b_slot, fast;
     int th, ntiles;                                            // pixel tile: th whole image rows (th * W <= 304), ntiles of them
     int npad, a_bytes;                                         // output channels per CTA (64 or 128) and bytes of its [W_hi | W_lo] stage
+    int cluster;                                               // 1: the K slices of an item are the CTAs of one cluster; they reduce through DSMEM
     int ntaps[kMaxBatch];
     int tap_list[kMaxBatch][9];
     float slope, out_mul;
@@ -48,6 +49,20 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t adesc, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// fp32 load from the shared memory of CTA `rank` of this cluster, at the address `local` has in this CTA
+__device__ __forceinline__ float ld_dsmem(uint32_t local, uint32_t rank)
+{
+    uint32_t ra;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
 }
 
 struct Item { int z, g, s0, s1, ks, tile; };
@@ -210,7 +225,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) conv_wt_kernel(const __grid_con
             const int co = I.g * prm.npad + q * 32 + lane;
             const bool live = q * 32 + lane < prm.npad && co < prm.cout;   // narrow groups: the MMA's upper rows read past W and are dropped
             float sc = 1.0f, sh = 0.0f;
-            if (prm.ksplit == 1 && live) { sc = __ldg(pr.scale + co); sh = __ldg(pr.shift + co); }
+            if (prm.ksplit == 1 && live && !prm.cluster) { sc = __ldg(pr.scale + co); sh = __ldg(pr.shift + co); }
             mbar_wait(acc_full, acc_phase);
             tc_fence_after();
             acc_phase ^= 1u;
@@ -221,6 +236,12 @@ __global__ void __launch_bounds__(kWtThreads, 1) conv_wt_kernel(const __grid_con
                 uint32_t v[16];
                 tmem_ld16(lane_base + (uint32_t)n0, v);
                 tmem_ld_wait();
+                if (prm.cluster) {                               // this K slice's partial sums -> shared memory [pixel][128 channels]
+                    float *part = reinterpret_cast<float *>(smem) + (size_t)n0 * 128 + q * 32 + lane;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) part[c * 128] = __uint_as_float(v[c]);
+                    continue;
+                }
                 if (!live) continue;
                 if (prm.ksplit > 1) {                           // raw partial sums: [ks][pixel][cpad]
                     float *o = pr.out + ((size_t)I.ks * prm.npix + p0 + n0) * prm.cpad + co;
@@ -250,6 +271,41 @@ __global__ void __launch_bounds__(kWtThreads, 1) conv_wt_kernel(const __grid_con
             tc_fence_before();
             mbar_arrive(acc_empty);
         }
+    }
+    if (prm.cluster) {
+        // Split-K inside a cluster: every CTA of the cluster holds the partial sums of its K slice in shared memory; CTA r
+        // sums pixels [r * per, (r + 1) * per) over all slices in slice order (deterministic) through distributed shared
+        // memory, applies the layer's epilogue and stores -- no scratch round trip, no reduction launch.
+        cluster_sync();
+        const Item I = decode(prm, begin);                       // grid == items: this CTA's only item
+        const Problem &pr = prm.p[I.z];
+        const int ks = prm.ksplit, per = (prm.npad_n + ks - 1) / ks;
+        const int nb = I.ks * per, ne = min(nb + per, prm.npad_n);
+        const int ch = threadIdx.x & 127, sub = threadIdx.x >> 7;
+        const int co = I.g * prm.npad + ch;
+        const int p0 = I.tile * prm.th * prm.W;
+        int pend = p0 + prm.th * prm.W;
+        if (pend > prm.npix) pend = prm.npix;
+        if (threadIdx.x < 512 && ch < prm.npad && co < prm.cout) {
+            const float sc = __ldg(pr.scale + co), sh = __ldg(pr.shift + co);
+            for (int n = nb + sub; n < ne; n += 4) {
+                const int p = p0 + n;
+                if (p >= pend) break;
+                const uint32_t la = base + (uint32_t)(n * 128 + ch) * 4u;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = j < ks ? ld_dsmem(la, (uint32_t)j) : 0.0f;
+                const float res = pr.residual ? __ldg(pr.residual + (size_t)p * pr.res_stride + co) : 0.0f;
+                float a = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a += v[j];
+                float r = fmaf(a, sc, sh);
+                if (prm.act == kSigmoidMul) r = res / (1.0f + expf(-r));
+                else r = activate(r + res, prm.act, prm.slope);
+                pr.out[(size_t)p * pr.out_stride + pr.out_coff + co] = r * prm.out_mul;
+            }
+        }
+        cluster_sync();                                          // nobody leaves while its shared memory is still being read
     }
     tc_fence_before();
     __syncthreads();
@@ -346,11 +402,23 @@ int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, 
         if ((size_t)ks * per_split > scratch_bytes) ks = (int)(scratch_bytes / per_split);
         if (ks >= 2) prm.ksplit = ks;
     }
+    // Experiment (flag 524288): K slices as the CTAs of a cluster (<= 8, portable) that reduce through distributed shared
+    // memory instead of the scratch + reduction launch.  Correct (tests/test_gpu_conv_tc.py runs it), but measured SLOWER on
+    // B200 than the separate, programmatically launched reduction: 15x20 1024 -> 256: 16.9 vs 15.0 us, 30x40 128 -> 512: 27.5
+    // vs 15.7 us, 3x3 30x40 256 -> 128 x4: 50.6 vs 28.1 us (clusters of 7 on 18-SM GPCs run in two waves; gang scheduling
+    // of 226 KB CTAs waits for whole groups of free SMs), AdapNet++ 2.11 vs 1.88 ms.  Off by default.
+    if ((flags & 524288) && !(flags & 4096)) {
+        int kc = min_steps / 2;
+        const int room = (int)(tc::sm_count() / items);
+        if (kc > room) kc = room;
+        if (kc > 8) kc = 8;
+        if (kc >= 2 && ((min_steps + kc - 1) / kc <= 6 || prm.ksplit <= kc)) { prm.ksplit = kc; prm.cluster = 1; }
+    }
     // long 1x1 K loops over many pixel tiles: the pixel-major kernel shares each weight stage between pixel tiles and wins
     // (measured: 60x80, 256 -> 256: 20 us there, 32 us here)
     if (ntiles > 1 && taps == 1 && min_steps / prm.ksplit > 6) return OJDF_SS_DECLINED;
     tc::SplitReduce red[tc::kMaxBatch];
-    if (prm.ksplit > 1)
+    if (prm.ksplit > 1 && !prm.cluster)
         for (int i = 0; i < n_problems; ++i) {
             const ojdf_conv_problem &q = problems_host[i];
             float *part = scratch_dev + (size_t)i * prm.ksplit * npix * prm.cpad;
@@ -365,19 +433,24 @@ int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, 
     }
     const long long total = items * prm.ksplit;
     int grid = tc::sm_count();
-    if (grid > total) grid = (int)total;
+    if (grid > total || prm.cluster) grid = (int)total;         // cluster mode: one item per CTA, consecutive CTAs = one cluster
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(wt::kWtThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = (flags & 8192) ? 0 : 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = (unsigned)prm.ksplit;
+    at[1].val.clusterDim.y = 1;
+    at[1].val.clusterDim.z = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = prm.cluster ? 2 : 1;
     const cudaError_t le = cudaLaunchKernelEx(&cfg, wt::conv_wt_kernel, prm);
     if (le != cudaSuccess) { cudaGetLastError(); return (int)le; }
+    if (prm.cluster) return launched(1);
     if (prm.ksplit > 1) {
         const int r = launched(1);
         if (r) return r;

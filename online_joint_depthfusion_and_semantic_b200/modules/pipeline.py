@@ -241,7 +241,15 @@ class Pipeline(nn.Module):
         pack = self._pack_target(frame, sem_ids) if frame.is_cuda else None
         values = self._extractor.forward(frame, batch['extrinsics'], batch['intrinsics'], volume['current'],
                                          volume['weights'], volume['origin'], volume['resolution'], rays=rays, pack=pack)
-        tsdf_est = self._fusion(self._prepare_fusion_input(frame, values, sem_ids), values, packed=pack is not None)
+        if pack is not None:
+            # the gather already wrote FusionNet's input rows: only views of the two per-pixel frames are handed over (the
+            # NCHW copies of modules/pipeline.py:74-102 would be four launches nobody reads)
+            inputs = {'tsdf_frame': frame.unsqueeze(1)}
+            if pack[3] is not None:
+                inputs['semantic_frame'] = pack[3].view(frame.shape).unsqueeze(1)
+        else:
+            inputs = self._prepare_fusion_input(frame, values, sem_ids)
+        tsdf_est = self._fusion(inputs, values, packed=pack is not None)
         sem = self.config.DATA.semantics
         if sem:
             sem_ids = sem_ids.type(torch.uint8)

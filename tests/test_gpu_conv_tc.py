@@ -40,6 +40,13 @@ CASES = [
     ('3x3 15x20 512 -> 256 split K finished inside the kernel (flag 16384)', 15, 20, 512, 256, 9, 4, 512, 256, 0, 1, True, 4, 0, 16384),
     ('1x1 15x20 1024 -> 256 split K inside the kernel, sigmoid gate (act 5)', 15, 20, 1024, 256, 1, 1, 1024, 256, 0, 5, True, 2, 0, 16384),
     ('3x3 30x40 48 -> 48 sigmoid gate (act 5) on the shared-memory-operand kernel', 30, 40, 48, 48, 9, 1, 48, 48, 0, 5, True, 1, 0, 0),
+    # the swapped-operand kernel (csrc/ojdf_conv_wt.cu): pixel tiles, 64-channel groups, strided output offset, and its
+    # cluster / distributed-shared-memory split-K experiment (flag 524288)
+    ('wt: 1x1 30x40 128 -> 512 residual, two problems', 30, 40, 128, 512, 1, 1, 128, 512, 0, 1, True, 2, 0, 0),
+    ('wt: 3x3 30x40 280 -> 256 five pixel tiles', 30, 40, 280, 256, 9, 1, 280, 256, 0, 1, False, 1, 0, 0),
+    ('wt: 3x3 60x80 64 -> 64 (64-channel group), dilation 2', 60, 80, 64, 64, 9, 2, 64, 64, 0, 1, False, 2, 0, 0),
+    ('wt: 1x1 15x20 1024 -> 256 cluster split K (flag 524288)', 15, 20, 1024, 256, 1, 1, 1024, 512, 0, 1, True, 2, 0, 524288),
+    ('wt: 3x3 23x37 96 -> 128 ragged map, cluster split K, sigmoid gate', 23, 37, 96, 128, 9, 3, 96, 128, 0, 5, True, 2, 0, 524288),
 ]
 
 
