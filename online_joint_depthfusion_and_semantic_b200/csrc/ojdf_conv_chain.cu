@@ -15,7 +15,9 @@
 // Same numerics as the layer kernels: kind::tf32, x = hi + lo, hi*hi + lo*hi + hi*lo, fp32 accumulation.
 //
 // Tensor memory (512 columns): D0 = [0,128), D1 = [128,256), A_hi = [256,384), A_lo = [384,512): one tile in flight
-// per CTA; the tensor pipe and the epilogue warps alternate.  Warps: 0 = TMA producer of the input boxes, 1 = producer
+// per CTA.  When consecutive steps use different accumulators the issuer starts the next step's MMAs on K chunk kc
+// (32 columns of A) as soon as the epilogue has written that chunk (four a_ready barriers), so the tensor pipe works
+// on layer l+1 while the epilogue warps are still converting layer l; otherwise the two alternate.  Warps: 0 = TMA producer of the input boxes, 1 = producer
 // of the weight stages (one stage = [W_hi | W_lo] of one 32-channel K chunk, streamed from L2 for every tile), 2 = MMA
 // issuer (owns the TMEM allocation), 4..11 = epilogue / hi-lo split, 12..15 = lo pass over the input boxes.
 #include <cstring>
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(kCThreads, 1) conv_chain_kernel(const __grid_c
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_bars[3 * kIS + 2 * kBS + 2];
+    __shared__ __align__(8) uint64_t s_bars[3 * kIS + 2 * kBS + 2 + 4];
     __shared__ uint32_t s_tmem;
     __shared__ float2 s_ss[128];
 
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(kCThreads, 1) conv_chain_kernel(const __grid_c
     auto b_full = [&](int s) { return bar0 + 8u * (3 * kIS + s); };
     auto b_empty = [&](int s) { return bar0 + 8u * (3 * kIS + kBS + s); };
     const uint32_t acc_full = bar0 + 8u * (3 * kIS + 2 * kBS), epi_done = acc_full + 8u;
+    auto a_ready = [&](int kc) { return epi_done + 8u + 8u * kc; };   // K chunk kc (32 columns) of the next step's A operand is in tensor memory
 
     const int tiles = prm.tiles_x * prm.tiles_y;
     const int total = prm.nz * tiles;
@@ -115,6 +118,7 @@ __global__ void __launch_bounds__(kCThreads, 1) conv_chain_kernel(const __grid_c
         for (int s = 0; s < kBS; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         mbar_init(acc_full, 1);
         mbar_init(epi_done, kEpiThreads);
+        for (int kc = 0; kc < 4; ++kc) mbar_init(a_ready(kc), kEpiThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -170,10 +174,17 @@ __global__ void __launch_bounds__(kCThreads, 1) conv_chain_kernel(const __grid_c
     } else if (warp == 2) {
         // ------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
         Ring rs(kIS), rb(kBS);
-        uint32_t epi_phase = 0;
+        uint32_t epi_phase = 0, a_phase = 0;
+        bool epi_pending = false;                                // an "activation -> next A" epilogue is running: this step's K chunks
+        int a_chunks = 0;                                        // start as soon as theirs is written (a_ready), not after all of it
         for (int it = begin; it < end; ++it) {
             for (int s = 0; s < prm.nsteps; ++s) {
                 const Step &S = prm.st[s];
+                if (epi_pending && S.src >= 0) {                 // a shared-memory step does not read A, but it may overwrite the
+                    mbar_wait(epi_done, epi_phase);              // accumulator that epilogue is still reading
+                    tc_fence_after();
+                    epi_phase ^= 1u; a_phase ^= 1u; epi_pending = false;
+                }
                 const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
                 const uint32_t acc = tmem + kColD + (uint32_t)S.acc * 128u;
                 const uint32_t b_lo_off = (uint32_t)S.npad * 128u;
@@ -206,6 +217,11 @@ __global__ void __launch_bounds__(kCThreads, 1) conv_chain_kernel(const __grid_c
                         __syncwarp();
                         rs.next();
                     } else {
+                        if (epi_pending) {
+                            if (kc < a_chunks) mbar_wait(a_ready(kc), a_phase);
+                            else mbar_wait(epi_done, epi_phase ^ 0u);   // (never taken: a step reads no more chunks than were written)
+                            tc_fence_after();
+                        }
                         const uint32_t a_hi = tmem + kColAhi + (uint32_t)(kc * kBK), a_lo = tmem + kColAlo + (uint32_t)(kc * kBK);
                         if (elect_one()) {
                             for (int k = 0; k < ksteps; ++k) {
@@ -225,13 +241,25 @@ __global__ void __launch_bounds__(kCThreads, 1) conv_chain_kernel(const __grid_c
                     __syncwarp();
                     rb.next();
                 }
-                if (S.epi) {
-                    // the epilogue warps read this accumulator (and may rewrite A): nothing is issued until they are done
-                    if (elect_one()) umma_commit(acc_full);
-                    __syncwarp();
+                if (epi_pending) {                                // all K chunks of this step were issued: that epilogue is complete
                     mbar_wait(epi_done, epi_phase);
                     tc_fence_after();
-                    epi_phase ^= 1u;
+                    epi_phase ^= 1u; a_phase ^= 1u; epi_pending = false;
+                }
+                if (S.epi) {
+                    if (elect_one()) umma_commit(acc_full);
+                    __syncwarp();
+                    if (S.epi == 1 && s + 1 < prm.nsteps && prm.st[s + 1].src < 0 && prm.st[s + 1].acc != S.acc) {
+                        // the next step reads this epilogue's output chunk by chunk into the OTHER accumulator
+                        epi_pending = true;
+                        a_chunks = (S.npad + 31) / 32;
+                    } else {
+                        // the epilogue warps read this accumulator (and may rewrite A): nothing is issued until they are done
+                        mbar_wait(epi_done, epi_phase);
+                        tc_fence_after();
+                        epi_phase ^= 1u;
+                        if (S.epi == 1) a_phase ^= 1u;           // the four a_ready barriers complete one phase per "-> next A" epilogue
+                    }
                 }
             }
         }
@@ -288,24 +316,35 @@ __global__ void __launch_bounds__(kCThreads, 1) conv_chain_kernel(const __grid_c
                 acc_phase ^= 1u;
                 const uint32_t tacc = lane_base + kColD + (uint32_t)S.acc * 128u;
                 if (S.epi == 1) {
-                    for (int n0 = half * 16; n0 < npad; n0 += 32) {
-                        uint32_t v[16];
-                        tmem_ld16(tacc + (uint32_t)n0, v);
-                        tmem_ld_wait();
-                        float o[16];
-                        chunk_any(S.act, v, o, s_ss + n0, S.slope, 1.0f);
-                        uint32_t hi[16], lo[16];
+                    // all accumulator chunks of this thread are requested at once; then chunk by chunk: activation, hi / lo
+                    // split, store, and the K chunk is announced (the issuer starts the next layer's MMAs on it)
+                    uint32_t v[4][16];
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            const uint32_t x = __float_as_uint(o[c]);
-                            hi[c] = x & 0xFFFFE000u;
-                            lo[c] = __float_as_uint(o[c] - __uint_as_float(hi[c]));
+                    for (int i = 0; i < 4; ++i)
+                        if (half * 16 + 32 * i < npad) tmem_ld16(tacc + (uint32_t)(half * 16 + 32 * i), v[i]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int n0 = half * 16 + 32 * i;
+                        if (32 * i >= npad) break;                       // (uniform: both halves of a 32-column chunk arrive together)
+                        if (n0 < npad) {
+                            float o[16];
+                            chunk_any(S.act, v[i], o, s_ss + n0, S.slope, 1.0f);
+                            uint32_t hi[16], lo[16];
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) {
+                                const uint32_t x = __float_as_uint(o[c]);
+                                hi[c] = x & 0xFFFFE000u;
+                                lo[c] = __float_as_uint(o[c] - __uint_as_float(hi[c]));
+                            }
+                            tmem_st16(lane_base + kColAhi + (uint32_t)n0, hi);
+                            tmem_st16(lane_base + kColAlo + (uint32_t)n0, lo);
+                            tmem_st_wait();
                         }
-                        tmem_st16(lane_base + kColAhi + (uint32_t)n0, hi);
-                        tmem_st16(lane_base + kColAlo + (uint32_t)n0, lo);
+                        tc_fence_before();
+                        mbar_arrive(a_ready(i));
                     }
-                    tmem_st_wait();
-                    tc_fence_before();
+                    for (int i = (npad + 31) / 32; i < 4; ++i) mbar_arrive(a_ready(i));   // unused chunks: keep the four phases in step
                     mbar_arrive(epi_done);
                 } else {
                     const int x = col * kBW + tx, y = row * kBH + ty;

@@ -317,7 +317,8 @@ class FusionNetEngine:
         cur, cs = vout, Cs
         if self.chain and all(c.cout <= 128 for c in pred) and len(pred) <= 12:
             # the whole Pred stack as one chain launch: activations stay in tensor memory between the eleven layers
-            steps = [ChainStep(_ptrs([c.weights_tc]), _ptrs([c.scale]), _ptrs([c.shift]), 0 if i == 0 else -1, c.cin, c.cout, 0, 1,
+            # accumulators alternate: the MMAs of layer i+1 start on the K chunks of layer i's output as they are written
+            steps = [ChainStep(_ptrs([c.weights_tc]), _ptrs([c.scale]), _ptrs([c.shift]), 0 if i == 0 else -1, c.cin, c.cout, i % 2, 1,
                                2 if i == len(pred) - 1 else 1, c.act, c.slope) for i, c in enumerate(pred)]
             self.chain_step([ChainInput(_ptrs([vout]), Cs, pred[0].cin)], steps, 1, [self.est], [0], self.P, self.scale)
             pred = []

@@ -38,8 +38,11 @@ def _launch(inputs, steps, nz, H, W, outs, coffs, ostride, out_mul, flags):
     return rc
 
 
+@pytest.mark.parametrize('alternate', [0, 1])
 @pytest.mark.parametrize('H,W,nz', [(8, 16, 1), (48, 64, 1), (37, 53, 2), (240, 320, 1)])
-def test_pred_chain_matches_fp64(H, W, nz):
+def test_pred_chain_matches_fp64(H, W, nz, alternate):
+    """alternate = 1: consecutive layers use different accumulators (the next layer's MMAs overlap the epilogue chunk by
+    chunk); 0: one accumulator (tensor pipe and epilogue warps alternate)."""
     g = torch.Generator().manual_seed(H * 1000 + W + nz)
     widths = [114, 95, 95, 76, 76, 57, 57, 38, 38, 19, 19, 9]
     acts = [2] * 10 + [3]
@@ -58,8 +61,8 @@ def test_pred_chain_matches_fp64(H, W, nz):
     steps = []
     for i in range(11):
         steps.append(ChainStep(_ptrs([layers[z][i][3] for z in range(nz)]), _ptrs([layers[z][i][4] for z in range(nz)]),
-                               _ptrs([layers[z][i][5] for z in range(nz)]), 0 if i == 0 else -1, widths[i], widths[i + 1], 0, 1,
-                               2 if i == 10 else 1, acts[i], 0.01))
+                               _ptrs([layers[z][i][5] for z in range(nz)]), 0 if i == 0 else -1, widths[i], widths[i + 1],
+                               (i % 2) * alternate, 1, 2 if i == 10 else 1, acts[i], 0.01))
     assert _launch(inputs, steps, nz, H, W, outs, [0] * nz, 9, 0.25, 0) == 0
     for y, o in zip(refs, outs):
         assert float((o.cpu().double() - y).abs().max()) <= 5e-5 * float(y.abs().max())
