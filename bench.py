@@ -503,6 +503,7 @@ def run_train(args):
     device = torch.device('cuda', local)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = os.environ.get('OJDF_CUDNN_BENCHMARK', '1') != '0'   # fp32 algorithms picked by measurement
     dist = None
     if world > 1:
         import torch.distributed as dist

@@ -75,13 +75,28 @@ class Pred(nn.Module):
         return self.pred(x)
 
 
+class _Broadcast1x1(nn.Module):
+    """nn.Upsample(size, mode='bilinear', align_corners=True) of a 1x1 map (modules/model.py:110): every output pixel is the
+    input value exactly (the interpolation weights are 1 and 0), i.e. a broadcast.  Written as expand() its backward is a
+    plain sum; the library's bilinear backward instead adds all H*W gradients of a channel into ONE address with atomics
+    (50 ms per call at 240x320, 3/4 of a training frame, tools/train_profile.py).  No parameters: same state_dict."""
+
+    def __init__(self, size):
+        super().__init__()
+        self.size = tuple(size) if isinstance(size, (tuple, list)) else (int(size), int(size))
+
+    def forward(self, x):
+        assert x.shape[-2:] == (1, 1)
+        return x.expand(-1, -1, self.size[0], self.size[1]).contiguous()
+
+
 class VortexPooling(nn.Module):
     def __init__(self, in_chs, mid_chs, out_chs, feat_res):
         super().__init__()
         self.gave_pool = nn.Sequential(
             nn.AdaptiveAvgPool2d((1, 1)),
             _conv(in_chs, out_chs, 1),
-            nn.Upsample(size=feat_res, mode='bilinear', align_corners=True),
+            _Broadcast1x1(feat_res),
             nn.BatchNorm2d(num_features=out_chs))
         self.pool1 = nn.AvgPool2d(kernel_size=3, stride=1, padding=1)
         self.pool2 = nn.AvgPool2d(kernel_size=3, stride=1, padding=1)
