@@ -36,7 +36,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO] + sources()
+    extra = os.environ.get('OJDF_EXTRA_NVCC_FLAGS', '').split()      # e.g. -DOJDF_SS_PROFILE for the role profile of conv_ss
+    cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO] + sources()
     subprocess.check_call(cmd)
     return SO
 

@@ -68,6 +68,9 @@ CASES = [
     ('P: dense per-tap boxes', 240, 320, 114, 19, 9, 1, 120, 120, 100, 2, False, 2, 128 | 4 | 1),
     ('P: 19->19', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 128 | 1),
     ('P: 19->19 no MMA', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 128 | 16 | 1),
+    ('P: 19->19 no lo pass', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 128 | 32 | 1),
+    ('P: 19->19 neither', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 128 | 48 | 1),
+    ('P: 19->19 per-thread stores', 240, 320, 19, 19, 9, 1, 20, 20, 0, 2, False, 2, 128 | 8 | 1),
     ('P: 456->114', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 1),
     ('P: 456->114 no MMA', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 16 | 1),
     ('P: 456->114 neither', 240, 320, 456, 114, 1, 1, 456, 116, 0, 0, False, 2, 128 | 48 | 1),
@@ -155,6 +158,7 @@ def run_case(idx, timing):
         print('   block 0 cycles: producer total %d (wait src_empty %d, b_empty %d) | mma total %d (acc_empty %d, b_full %d, a_full %d) | '
               'split0 total %d (src_full %d, a_empty %d) | split1 total %d (src_full %d, a_empty %d) | epilogue total %d (acc_full %d)'
               % (p[2], p[0], p[1], p[6], p[3], p[4], p[5], p[9], p[7], p[8], p[12], p[10], p[11], p[14], p[13]), flush=True)
+        print('   raw role profile: %s' % ' '.join('%d:%d' % (i, v) for i, v in enumerate(p) if v), flush=True)
         if not (flags & 65536):
             print('   ss issuer: in the MMA issue blocks %d, in the weight-stage commits %d' % (p[8], p[10]), flush=True)
 
