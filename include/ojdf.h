@@ -270,18 +270,6 @@ typedef struct ojdf_pool_problem {
                                      * product comes out of the same merged launch as the pooled branches') */
 } ojdf_pool_problem;
 int ojdf_avgpool3_batched(const ojdf_pool_problem *problems_host, int n_problems, int H, int W, int C, int relu, void *stream);
-/* All cascaded pools of up to two VortexPooling blocks in ONE launch (modules/model.py:143-155): y_dev holds the bare first-layer
- * products of the four branches side by side (4 groups of C channels per pixel, C % 4 == 0, C <= 32); branch b receives
- * out_b = relu(scale_b * pool^b(y_b) + shift_b) with pool = 3x3 / stride 1 / zero padding / divisor 9 applied b times
- * (b = 0: only the epilogue).  Replaces three ojdf_avgpool3_batched launches per block. */
-typedef struct ojdf_vortex_pool_problem {
-    const float *y_dev;
-    float *out_dev[4];
-    const float *scale_dev[4];
-    const float *shift_dev[4];
-    int y_stride, out_stride;
-} ojdf_vortex_pool_problem;
-int ojdf_vortex_pools(const ojdf_vortex_pool_problem *problems_host, int n_problems, int H, int W, int C, void *stream);
 /* VortexPooling global branch (modules/model.py:107-112) folded into the bias of the `final` 1x1 conv:
  * shift_out[co] = f_shift[co] + f_scale[co] * sum_c wf1[co,c] * (g_scale[c]*(wg[c,:].mean_pixels(in)) + g_shift[c]).
  * partial_dev: scratch of partial_blocks*C floats. */

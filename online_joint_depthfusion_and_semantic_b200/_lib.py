@@ -40,7 +40,6 @@ _SIGNATURES = {
     'ojdf_avgpool3_batched': (_i, [_vp, _i, _i, _i, _i, _i, _vp]),
     'ojdf_vortex_bias': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp]),
     'ojdf_gap_bias': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp]),
-    'ojdf_vortex_pools': (_i, [_vp, _i, _i, _i, _i, _vp]),
     'ojdf_conv_chain': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _i, _vp]),
     'ojdf_adapnet_skip_join': (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
     'ojdf_nchw_to_nhwc': (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),

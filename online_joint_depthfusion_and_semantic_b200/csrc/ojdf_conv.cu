@@ -170,75 +170,6 @@ avgpool3_batched_kernel(PoolBatch batch, int H, int W, int C, int relu)
     reinterpret_cast<float4 *>(pr.out + (size_t)p * pr.out_stride)[c4] = o;
 }
 
-// VortexPooling's cascaded pools in ONE launch (modules/model.py:143-155): branch b (0..3) of a problem sees
-// pool^b(W_b . x); this kernel takes the merged product buffer (4 groups of C channels per pixel), runs b passes of the
-// 3x3 / stride 1 / zero-padded average (divisor 9, intermediate values outside the image are zero, exactly like three
-// nn.AvgPool2d in a row) on a 16x16 tile with a halo of b pixels in shared memory, and finishes with the branch's
-// bias / BatchNorm / ReLU.  Grid (tiles_x, tiles_y, problems * 4).
-struct VortexPoolProblem {
-    const float *y; float *out[4]; const float *scale[4]; const float *shift[4];
-    int y_stride, out_stride;
-};
-struct VortexPoolBatch { VortexPoolProblem p[2]; };
-constexpr int kVpTile = 16;
-
-__global__ void __launch_bounds__(256)
-vortex_pools_kernel(VortexPoolBatch batch, int H, int W, int C)
-{
-    extern __shared__ __align__(16) float vp_smem[];
-    const VortexPoolProblem &pr = batch.p[blockIdx.z >> 2];
-    const int b = blockIdx.z & 3;
-    const int c4n = C >> 2;
-    const int x0 = blockIdx.x * kVpTile, y0 = blockIdx.y * kVpTile;
-    const int side0 = kVpTile + 2 * b;
-    float4 *bufA = reinterpret_cast<float4 *>(vp_smem);
-    float4 *bufB = bufA + (size_t)(kVpTile + 6) * (kVpTile + 6) * c4n;
-    // load the tile + halo of branch b's group (zero outside the image)
-    for (int i = threadIdx.x; i < side0 * side0 * c4n; i += blockDim.x) {
-        const int c4 = i % c4n, q = i / c4n, ly = q / side0, lx = q - ly * side0;
-        const int y = y0 - b + ly, x = x0 - b + lx;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(reinterpret_cast<const float4 *>(pr.y + (size_t)(y * W + x) * pr.y_stride + b * C) + c4);
-        bufA[i] = v;
-    }
-    __syncthreads();
-    float4 *src = bufA, *dst = bufB;
-    int side = side0;
-    for (int k = 0; k < b; ++k) {                               // one pooling pass: side -> side - 2
-        const int so = side - 2, r = b - k - 1;                  // output region: tile + halo of r pixels
-        for (int i = threadIdx.x; i < so * so * c4n; i += blockDim.x) {
-            const int c4 = i % c4n, q = i / c4n, ly = q / so, lx = q - ly * so;
-            const int y = y0 - r + ly, x = x0 - r + lx;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (y >= 0 && y < H && x >= 0 && x < W) {
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const float4 v = src[((ly + dy) * side + lx + dx) * c4n + c4];
-                        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-                    }
-                a = make_float4(a.x / 9.0f, a.y / 9.0f, a.z / 9.0f, a.w / 9.0f);
-            }
-            dst[i] = a;
-        }
-        __syncthreads();
-        float4 *t = src; src = dst; dst = t;
-        side = so;
-    }
-    // epilogue on the 16x16 tile (side == kVpTile now)
-    for (int i = threadIdx.x; i < kVpTile * kVpTile * c4n; i += blockDim.x) {
-        const int c4 = i % c4n, q = i / c4n, ly = q / kVpTile, lx = q - ly * kVpTile;
-        const int y = y0 + ly, x = x0 + lx;
-        if (y >= H || x >= W) continue;
-        float4 o = src[i];
-        const float4 sc = __ldg(reinterpret_cast<const float4 *>(pr.scale[b]) + c4), sh = __ldg(reinterpret_cast<const float4 *>(pr.shift[b]) + c4);
-        o.x = fmaxf(fmaf(o.x, sc.x, sh.x), 0.f); o.y = fmaxf(fmaf(o.y, sc.y, sh.y), 0.f);
-        o.z = fmaxf(fmaf(o.z, sc.z, sh.z), 0.f); o.w = fmaxf(fmaf(o.w, sc.w, sh.w), 0.f);
-        reinterpret_cast<float4 *>(pr.out[b] + (size_t)(y * W + x) * pr.out_stride)[c4] = o;
-    }
-}
-
 // Per-channel sums over all pixels (global average pool numerator): block b sums its contiguous slice of
 // pixels with float4 loads (thread = one float4 column of one of `lanes` interleaved pixels), folds the
 // pixel lanes through shared memory in a fixed order and writes partial[b][C]; the tiny second stage runs
@@ -594,33 +525,6 @@ extern "C" int ojdf_avgpool3_batched(const ojdf_pool_problem *problems_host, int
     }
     const long long n = (long long)H * W * (C >> 2);
     avgpool3_batched_kernel<<<dim3((unsigned)((n + 255) / 256), n_problems), 256, 0, (cudaStream_t)stream>>>(b, H, W, C, relu);
-    return launched(1);
-}
-
-extern "C" int ojdf_vortex_pools(const ojdf_vortex_pool_problem *problems_host, int n_problems, int H, int W, int C, void *stream)
-{
-    if (!problems_host || n_problems < 1 || n_problems > 2 || H < 1 || W < 1 || C < 4 || C > 32 || (C & 3)) return OJDF_ERR_BADARG;
-    VortexPoolBatch bt;
-    for (int i = 0; i < 2; ++i) {
-        const ojdf_vortex_pool_problem &q = problems_host[i < n_problems ? i : 0];
-        if (!q.y_dev || (q.y_stride & 3) || q.y_stride < 4 * C || (q.out_stride & 3) || q.out_stride < C || ((uintptr_t)q.y_dev & 15))
-            return OJDF_ERR_BADARG;
-        bt.p[i].y = q.y_dev; bt.p[i].y_stride = q.y_stride; bt.p[i].out_stride = q.out_stride;
-        for (int b = 0; b < 4; ++b) {
-            if (!q.out_dev[b] || !q.scale_dev[b] || !q.shift_dev[b] || ((uintptr_t)q.out_dev[b] & 15) || ((uintptr_t)q.scale_dev[b] & 15) ||
-                ((uintptr_t)q.shift_dev[b] & 15))
-                return OJDF_ERR_BADARG;
-            bt.p[i].out[b] = q.out_dev[b]; bt.p[i].scale[b] = q.scale_dev[b]; bt.p[i].shift[b] = q.shift_dev[b];
-        }
-    }
-    const size_t smem = (size_t)((kVpTile + 6) * (kVpTile + 6) + (kVpTile + 4) * (kVpTile + 4)) * C * sizeof(float);
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaFuncSetAttribute(vortex_pools_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
-    }
-    const dim3 grid((W + kVpTile - 1) / kVpTile, (H + kVpTile - 1) / kVpTile, n_problems * 4);
-    vortex_pools_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(bt, H, W, C);
     return launched(1);
 }
 

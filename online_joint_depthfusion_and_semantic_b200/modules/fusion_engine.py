@@ -61,12 +61,6 @@ class ConvProblem(C.Structure):
                 ('in_width', C.c_int), ('out_step', C.c_int), ('out_width', C.c_int), ('tap_mask', C.c_int)]
 
 
-class VortexPoolProblem(C.Structure):
-    """include/ojdf.h: ojdf_vortex_pool_problem."""
-    _fields_ = [('y_dev', C.c_void_p), ('out_dev', C.c_void_p * 4), ('scale_dev', C.c_void_p * 4), ('shift_dev', C.c_void_p * 4),
-                ('y_stride', C.c_int), ('out_stride', C.c_int)]
-
-
 class ChainInput(C.Structure):
     """include/ojdf.h: ojdf_chain_input."""
     _fields_ = [('in_dev', C.c_void_p * 2), ('in_stride', C.c_int), ('cin', C.c_int)]
@@ -243,9 +237,11 @@ class FusionNetEngine:
             cin, Cv = vs[0].cin, vs[0].cout
             ps, Cvp = _pad4(cin), _pad4(Cv)
             tb = [[[z(mid_s) for _ in range(2)] for _ in range(4)] for _ in range(n)]
+            P1 = [[None, None] + [z(mid_s) for _ in range(2)] for _ in range(n)]   # pool(Y_b), b = 2, 3
+            P2 = [z(mid_s) for _ in range(n)]                                       # pool(pool(Y_3))
             chained = self.chain and n <= 2 and Cv <= 128
             br_out = [None if chained else z(4 * Cvp) for _ in range(n)]   # the chain launch never materialises the branch outputs
-            self._keep += [tb, br_out]
+            self._keep += [tb, P1, P2, br_out]
             # global-pool branch -> bias of the final conv: a long, thin reduction (two launches, one of them a single
             # block) that only the LAST conv of the vortex needs: it runs on a side stream next to the branch convolutions
             self.plan.append(('fork_bias',))
@@ -258,12 +254,26 @@ class FusionNetEngine:
             self._keep.append(Yall)
             conv_step([(vs[i].raw_all, vs[i].raw_all.problem(srcs[i], src_stride, Yall[i], 4 * mid_s)) for i in range(n)])
 
-            # all cascaded pools (branch b: b passes of the 3x3 average, then bias / BatchNorm / ReLU) of the n blocks: one launch
-            p4 = lambda ts: (C.c_void_p * 4)(*[t.data_ptr() for t in ts])   # noqa: E731
-            vp = (VortexPoolProblem * n)(*[VortexPoolProblem(Yall[i].data_ptr(), p4([tb[i][b][0] for b in range(4)]),
-                                                            p4([vs[i].post[b][0] for b in range(4)]), p4([vs[i].post[b][1] for b in range(4)]),
-                                                            4 * mid_s, mid_s) for i in range(n)])
-            self.plan.append(('vpools', vp, n, mid_s))
+            def pool_step(items):
+                """items: (src, dst, (scale, shift) or None[, identity]) with src = tensor or (tensor, channel offset, stride);
+                one launch, ReLU where an epilogue is given."""
+                probs = []
+                for it in items:
+                    a, d, e = it[:3]
+                    ident = int(it[3]) if len(it) > 3 else 0
+                    ptr, stride = (a[0].data_ptr() + 4 * a[1], a[2]) if isinstance(a, tuple) else (a.data_ptr(), mid_s)
+                    probs.append(PoolProblem(ptr, d.data_ptr(), e[0].data_ptr() if e else None, e[1].data_ptr() if e else None,
+                                             stride, mid_s, ident))
+                arr = (PoolProblem * len(items))(*probs)
+                self._keep.append([it[2] for it in items])
+                self.plan.append(('pools', arr, len(items), mid_s))
+
+            ysl = lambda i, b: (Yall[i], b * mid_s, 4 * mid_s)   # noqa: E731  (branch b's product inside the merged buffer)
+            pool_step([(ysl(i, 0), tb[i][0][0], vs[i].post[0], 1) for i in range(n)] +
+                      [(ysl(i, 1), tb[i][1][0], vs[i].post[1]) for i in range(n)] +
+                      [(ysl(i, b), P1[i][b], None) for i in range(n) for b in (2, 3)])
+            pool_step([(P1[i][2], tb[i][2][0], vs[i].post[2]) for i in range(n)] + [(P1[i][3], P2[i], None) for i in range(n)])
+            pool_step([(P2[i], tb[i][3][0], vs[i].post[3]) for i in range(n)])
             conv_step([(vs[i].branches[b][1], vs[i].branches[b][1].problem(tb[i][b][0], mid_s, tb[i][b][1], mid_s))
                        for i in range(n) for b in range(4)])
             conv_step([(vs[i].branches[b][2], vs[i].branches[b][2].problem(tb[i][b][1], mid_s, tb[i][b][0], mid_s))
@@ -366,9 +376,6 @@ class FusionNetEngine:
                 elif kind == 'chain':
                     _, ia, ni, sa, ns, nz, op, oc, ostride, omul = step
                     _lib.check(L.ojdf_conv_chain(ia, ni, sa, ns, nz, H, W, op, oc, ostride, omul, self.flags, st))
-                elif kind == 'vpools':
-                    _, arr, n, ch = step
-                    _lib.check(L.ojdf_vortex_pools(arr, n, H, W, ch, st))
                 elif kind == 'pools':
                     _, arr, n, ch = step
                     _lib.check(L.ojdf_avgpool3_batched(arr, n, H, W, ch, 1, st))
