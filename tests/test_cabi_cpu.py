@@ -126,3 +126,40 @@ def test_conv_problem_struct_matches_header(tmp_path):
     out = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     assert out[0] == C.sizeof(ConvProblem)
     assert out[1:] == [getattr(ConvProblem, f).offset for f in fields]
+
+
+@pytest.mark.parametrize('ctype,cname', [('ChainInput', 'ojdf_chain_input'), ('ChainStep', 'ojdf_chain_step'),
+                                         ('PoolProblem', 'ojdf_pool_problem')])
+def test_other_problem_structs_match_header(tmp_path, ctype, cname):
+    """The ctypes mirrors of the chain / pool structs (modules/fusion_engine.py) against the C compiler's layout of include/ojdf.h."""
+    import subprocess
+    from online_joint_depthfusion_and_semantic_b200.modules import fusion_engine
+    T = getattr(fusion_engine, ctype)
+    fields = [f[0] for f in T._fields_]
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ojdf.h"\nint main(void) {\n'
+                   '  printf("%%zu", sizeof(%s));\n' % cname +
+                   ''.join('  printf(" %%zu", offsetof(%s, %s));\n' % (cname, f) for f in fields) +
+                   '  return 0;\n}\n')
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    out = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == C.sizeof(T)
+    assert out[1:] == [getattr(T, f).offset for f in fields]
+
+
+def test_chain_argument_checks_need_no_gpu():
+    """ojdf_conv_chain rejects malformed chains before touching the device."""
+    from online_joint_depthfusion_and_semantic_b200.modules.fusion_engine import ChainInput, ChainStep
+    L = _lib.lib()
+    assert L.ojdf_conv_chain(None, 1, None, 1, 1, 8, 16, None, None, 32, 1.0, 0, None) == -1
+    ia, sa = (ChainInput * 1)(), (ChainStep * 13)()
+    op, oc = (C.c_void_p * 1)(), (C.c_int * 1)()
+    assert L.ojdf_conv_chain(ia, 1, sa, 13, 1, 8, 16, op, oc, 32, 1.0, 0, None) == -1           # more than 12 steps
+    assert L.ojdf_conv_chain(ia, 1, sa, 1, 3, 8, 16, op, oc, 32, 1.0, 0, None) == -1            # more than 2 problems
+
+
+def test_frame_stream_needs_cuda():
+    from online_joint_depthfusion_and_semantic_b200.stream import FrameStream
+    with pytest.raises(ValueError):
+        FrameStream(None, None, 'cpu')
