@@ -130,10 +130,28 @@ class Pipeline(nn.Module):
             return self._segmentation_eager(image, aux)
         return self._graphed(self._segmentation_eager, image, aux)
 
+    def segment(self, batch, device=None):
+        """The 2-D segmentation of a frame on its own (modules/pipeline.py:181-184): private copies of (scores, ids u8, label
+        frame) that `fuse(..., semantics=...)` accepts in place of running AdapNet++ itself.  It only needs the batch, not
+        the volumes, so a streaming caller (stream.FrameStream) runs it for frame i+1 on a second stream while frame i is
+        still being extracted / fused / integrated.  None when the pipeline does not predict semantics."""
+        if not (self.config.DATA.semantics and self.config.DATA.semantic_strategy == 'predict'):
+            return None
+        if device is not None:
+            self.device = device
+        self._shape = batch['image'].shape
+        scores, ids = self._semantic_frame(batch, as_uint8=True)
+        frame = self._sem_frame
+        return {'scores': scores.clone(), 'ids': ids.clone(), 'sem_frame': None if frame is None else frame.clone()}
+
     def _semantic_frame(self, batch, as_uint8):
         """(scores f32, ids) per pixel, or (None, None): modules/pipeline.py:181-193,277-292."""
         if not self.config.DATA.semantics:
             return None, None
+        pre, self._pre_semantics = getattr(self, '_pre_semantics', None), None
+        if pre is not None:                                      # computed ahead by segment()
+            self._sem_frame = pre['sem_frame']
+            return pre['scores'], (pre['ids'] if as_uint8 else pre['ids'].long())
         strategy = self.config.DATA.semantic_strategy
         self._sem_frame = None
         if strategy == 'predict':
@@ -223,9 +241,11 @@ class Pipeline(nn.Module):
         return frame, torch.where(batch['mask'].to(self.device), frame, torch.zeros_like(frame))
 
     # ---- a1: inference step (modules/pipeline.py:173-248) -------------------------------------------
-    def fuse(self, batch, database, device):
+    def fuse(self, batch, database, device, semantics=None):
+        """`semantics`: optional result of segment(batch) (skips the AdapNet++ pass of this call)."""
         self.device = device
         self._shape = batch['image'].shape
+        self._pre_semantics = semantics
         frame, filtered_frame = self._frames(batch)
         scene_id = batch['frame_id'][0].split('/')[0]
         volume = database[scene_id]

@@ -176,14 +176,16 @@ def test_fuse_training_values_vs_reference_golden(golden):
     assert int(db.ids_est['synth0'].volume.count_nonzero()) == 0             # test=False: no semantic update
 
 
-def test_frame_stream_equals_synchronous_fuse():
-    """stream.FrameStream (pinned host frames, copies / read-backs overlapped with the kernels of the neighbouring frames)
+@pytest.mark.parametrize('strategy,use_sem', [('gt', False), ('predict', True)])
+def test_frame_stream_equals_synchronous_fuse(strategy, use_sem):
+    """stream.FrameStream (pinned host frames, copies / read-backs overlapped with the kernels of the neighbouring frames;
+    with predicted semantics also the AdapNet++ pass of frame i+1 on its own stream next to the fusion of frame i)
     leaves bit-identical volumes to calling Pipeline.fuse frame by frame, and returns every frame's result in order."""
     from online_joint_depthfusion_and_semantic_b200.stream import FrameStream
     h, w, G = 48, 64, 48
     vols, results = [], []
     for streamed in (False, True):
-        scene, cfg, pipe, db = _world(h, w, G, 'gt', False)
+        scene, cfg, pipe, db = _world(h, w, G, strategy, use_sem)
         last = {}
         inner = pipe._fusion
 
@@ -209,7 +211,9 @@ def test_frame_stream_equals_synchronous_fuse():
                     got.append(float(last['v'].item()))
         torch.cuda.synchronize()
         v = db['s0']
-        vols.append([v['current'].cpu().numpy().view(np.uint16).copy(), v['weights'].cpu().numpy().view(np.uint16).copy()])
+        vols.append([v['current'].cpu().numpy().view(np.uint16).copy(), v['weights'].cpu().numpy().view(np.uint16).copy()] +
+                    ([v['ids_est'].cpu().numpy().copy(), v['scores'].cpu().numpy().view(np.uint16).copy()] if use_sem else []))
         results.append(got)
     assert len(results[1]) == 5 and results[0] == results[1]
-    assert np.array_equal(vols[0][0], vols[1][0]) and np.array_equal(vols[0][1], vols[1][1])
+    for a, b in zip(vols[0], vols[1]):
+        assert np.array_equal(a, b)
