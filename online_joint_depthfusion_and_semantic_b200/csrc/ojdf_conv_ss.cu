@@ -139,7 +139,7 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity)
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "r"(bar), "r"(parity), "r"(OJDF_PARK_NS)
         : "memory");
     if (!done) mbar_wait(bar, parity);
 }

@@ -43,7 +43,7 @@ namespace tc {
 
 // Optional role profile (flag 128, block 0 only): cycles each role spent waiting per barrier class.
 __device__ long long g_prof[32];
-__device__ __forceinline__ void mbar_wait_p(uint32_t bar, uint32_t parity, int cls, bool on, uint32_t hint = 0x989680u)
+__device__ __forceinline__ void mbar_wait_p(uint32_t bar, uint32_t parity, int cls, bool on, uint32_t hint = OJDF_PARK_NS)
 {
     if (!on) {
         if (hint) mbar_wait(bar, parity, hint); else mbar_poll(bar, parity);
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int total = prm.nprob * prm.groups * prm.ksplit * tiles;
     const int begin = (int)((long long)total * blockIdx.x / gridDim.x);
     const int end = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
-    const uint32_t hot_hint = (prm.dbg & 1024) ? 0u : 0x989680u;   // experiment: do not park the A-ring waiters
+    const uint32_t hot_hint = (prm.dbg & 1024) ? 0u : OJDF_PARK_NS;   // experiment: do not park the A-ring waiters
     const bool halo_mode = prm.hd > 0 || prm.taps == 1;
     const int nbox = halo_mode ? 1 : prm.taps;                   // TMA boxes per K chunk
     const int taps_per_box = halo_mode ? prm.taps : 1;

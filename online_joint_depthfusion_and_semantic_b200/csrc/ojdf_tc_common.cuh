@@ -64,9 +64,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Suspend-time hint (ns) of the parked mbarrier waits.
+#ifndef OJDF_PARK_NS
+#define OJDF_PARK_NS 0x989680u
+#endif
 // Wait for a phase of an mbarrier.  try_wait with a suspend-time hint parks the warp in hardware (no issue
 // slots burnt by the many waiting roles); a pipeline that is wedged for ~2 s traps instead of hanging.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint = 0x989680u)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint = OJDF_PARK_NS)
 {
     uint32_t done = 0;
     for (int spins = 0;; ++spins) {
