@@ -46,7 +46,7 @@ def main(path, top=40, json_out=None):
     for k, s in list(summary.items())[:top]:
         print('%-84s %6d %10.1f %9.2f %5.1f%% %12s' % (k[:84], s['n'], s['sum_us'], s['mean_us'], 100 * s['share'],
                                                       '-' if s['dram_bytes_per_launch'] is None else '%.3f' % (s['dram_bytes_per_launch'] / 1e6)))
-    mine = {k: s for k, s in summary.items() if 'ojdf::' in k or 'tc::' in k or 'ss::' in k}
+    mine = {k: s for k, s in summary.items() if any(ns in k for ns in ('ojdf::', 'tc::', 'ss::', 'wt::', 'chain::'))}
     own = sum(s['sum_us'] for s in mine.values())
     print('\nown kernels (libojdf.so): %.1f us = %.2f%% of the captured time' % (own, 100 * own / tot))
     if json_out:

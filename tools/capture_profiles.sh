@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
     > gpurun_out/r2_bench_under_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'conv_ss_kernel|conv_tc_kernel|conv_chain_kernel' \
     -o gpurun_out/r2_conv_full -f python tools/fusionnet_bench.py --reps 1 --profile > gpurun_out/r2_conv_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'conv_wt_kernel' -s 260 -c 12 \
+ncu --set full --clock-control none --import-source on -k regex:'conv_wt_kernel' -s 66 -c 14 \
     -o gpurun_out/r2_wt_full -f python tools/adapnet_once.py > gpurun_out/r2_wt_full.log 2>&1
 ncu --set full --clock-control none --import-source on --profile-from-start off \
     -k regex:'extract_kernel|count_kernel|offsets_kernel|scatter_kernel|rank_kernel|apply_kernel' -c 8 \
