@@ -12,13 +12,16 @@ there is no dataset, checkpoint or network in this environment.
 Own arm (default): one process per GPU, scenes sharded one-per-rank (4 scenes per rank,
 rotated every frame so the voxel working set exceeds L2), no data-path collective.
   value  = frames/s with the frame tensors already resident in HBM
-  e2e    = frames/s through the same call with HOST (pinned) frame tensors: H2D of
-           image+depth+mask every step and a D2H read of the step's scalar result
-  roofline = the kernel the step spends most of its own-kernel time in: the tcgen05 tap GEMM
-           (csrc/ojdf_conv_tc.cu) of the FusionNet stack -- algorithmic conv FLOPs of FusionNet_v3(sem)
+  e2e    = frames/s through the streaming call (stream.FrameStream.submit -> Pipeline.fuse) with HOST (pinned) frame
+           tensors: H2D of image+depth+mask every step and a D2H read of a step's scalar result every step, overlapped
+           with the neighbouring frames' kernels (depth-2 ring, AdapNet++ of frame i+1 next to the fusion of frame i);
+           e2e.value_synchronous = the same with one blocking Pipeline.fuse + .item() per frame
+  roofline = the kernels the step spends most of its own-kernel time in: the tcgen05 convolutions (csrc/ojdf_conv_ss.cu,
+           ojdf_conv_tc.cu, ojdf_conv_chain.cu) of the FusionNet stack -- algorithmic conv FLOPs of FusionNet_v3(sem)
            (78.15 GFLOP per 240x320 frame) / the CUDA-event time of the engine forward,
            against the measured dense bf16 tensor peak (sustained figure: the kernel is timed inside
-           a long step); roofline_integrate / roofline_extract = algorithmic bytes (817 B per valid
+           a long step); roofline_adapnet = the same for AdapNet++ stage 2 (59.1 GFLOP, + ojdf_conv_wt.cu);
+           roofline_integrate / roofline_extract = algorithmic bytes (817 B per valid
            ray / 364 B per ray) / CUDA-event time of those calls, against the measured HBM peak
   cpu_baseline = the unmodified reference's Pipeline.fuse on the host CPU (kind "reference"; the CPU port --
            oracle C for extract/integrate + the same torch modules on CPU -- is reported beside it as

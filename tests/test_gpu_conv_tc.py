@@ -116,12 +116,13 @@ def test_conv_tc_rejects_bad_arguments():
     assert L.ojdf_conv_tc_batched(None, 1, 32, 32, 8, 16, 1, 0, 0.0, 1.0, 0, 0, None, 0, st) == -1
 
 
-def test_conv_tc_strided_input_matches_stride2_conv():
+@pytest.mark.parametrize('cout', [80, 128])
+def test_conv_tc_strided_input_matches_stride2_conv(cout):
     """in_step = 2: a 1x1 convolution with stride 2 (ResNet down-sampling, torchvision Bottleneck.downsample) and
     a stride-2 3x3 expressed as the stride-1 3x3 followed by a strided 1x1 read (modules/adapnet_engine.py)."""
     L = _lib.lib()
     g = torch.Generator().manual_seed(9)
-    Hin, Win, cin, cout = 30, 40, 96, 80
+    Hin, Win, cin = 30, 40, 96                  # cout 80: pixel-major kernel; 128: the swapped-operand kernel (ojdf_conv_wt.cu)
     Ho, Wo = Hin // 2, Win // 2
     x = torch.randn(Hin * Win, cin, generator=g)
     w = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
