@@ -394,7 +394,8 @@ int ojdf_conv_wt_launch(const ojdf_conv_problem *problems_host, int n_problems, 
     prm.ksplit = 1;
     prm.cpad = groups * npad;
     if (scratch_dev && !(flags & 4096)) {
-        int ks = min_steps / 2;
+        static const int steps_per_cta = [] { const char *e = getenv("OJDF_WT_STEPS"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+        int ks = min_steps / steps_per_cta;
         const int room = (int)(tc::sm_count() / items);
         if (ks > room) ks = room;
         if (ks > 32) ks = 32;
