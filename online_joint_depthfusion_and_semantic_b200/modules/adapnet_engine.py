@@ -1,8 +1,11 @@
 """Inference engines for AdapNet++ on libojdf's tensor-core tap-GEMM kernels.
 
 `AdapNetEngine` (bottom of this file) runs the whole network pixel-major: the 7x7 stem + BatchNorm + ReLU + max-pool is
-one own kernel (ojdf_adapnet_stem), everything else except the (optional) bilinear aux heads and the two tiny skip-join
-gates is a fused conv + BatchNorm + activation (+ residual) launch (csrc/ojdf_conv_tc.cu / ojdf_conv_ss.cu); stride-2
+one own kernel (ojdf_adapnet_stem), the two skip-join gates are ojdf_adapnet_skip_join, everything else except the
+(optional) bilinear aux heads is a fused conv + BatchNorm + activation (+ residual) launch of ojdf_conv_tc_batched, which
+picks csrc/ojdf_conv_wt.cu (>= 64 output channels on maps up to 256 pixels wide: channels as M, the image as N),
+ojdf_conv_ss.cu (3x3 with a halo box that fits shared memory) or ojdf_conv_tc.cu; the two skip SSMAs run on a side
+stream next to layer3 / layer4 / eASPP; stride-2
 layers are the stride-1 layer followed by a consumer that reads every other pixel (`in_step = 2`); the three transposed
 convolutions are 4 / 16 phase convolutions that write every 2nd / 4th output pixel (`out_step`, dead taps masked); the
 SSMA gate multiplies inside the epilogue of its sigmoid convolution; `segment()` adds the fused softmax / max / arg-max

@@ -1,20 +1,25 @@
-"""Inference engine for FusionNet_v2 / FusionNet_v3 on libojdf's fp32 tap-GEMM kernels.
+"""Inference engine for FusionNet_v2 / FusionNet_v3 on libojdf's tensor-core convolution kernels.
 
 The nn.Module in model.py owns the parameters (so checkpoints load exactly like the reference's,
 test_fusion.py:63-65); this class turns them into a launch plan over pixel-major (NHWC) buffers:
 
-  * per conv: weights re-laid out as [out-group of 20][tap][cin padded to 4][20], conv bias +
-    inference BatchNorm folded into a per-channel (scale, shift) epilogue, activation fused;
+  * per conv: weights packed once as swizzled shared-memory images (ojdf_conv_tc_pack_weights), conv bias +
+    inference BatchNorm folded on the host in f64 into a per-channel (scale, shift) epilogue, activation fused;
   * dense-block concatenation (modules/model.py:258-263) = channel offsets into one buffer;
-  * VortexPooling (modules/model.py:100-161): the 3 cascaded 3x3 average pools commute with the first 1x1 conv
-    of their branch, so the 19-channel product W.x is pooled (3 batched launches, BN + ReLU after the last pool)
-    instead of the 114-channel input; 4 dilated branches writing into one 4*C buffer; the global-pool branch
-    folded into the bias of the `final` 1x1 conv;
-  * Pred chain (modules/model.py:24-52) ends in tanh * output_scale and writes (N, n_points) f32 --
-    exactly the layout the integrator consumes, so no NCHW<->NHWC permutes exist anywhere.
+  * VortexPooling (modules/model.py:100-161): the first 1x1 convolution of all four branches is ONE launch (the bare
+    products W_b . x side by side); the 3 cascaded 3x3 average pools commute with that convolution, so the 19-channel
+    products are pooled (3 batched launches, bias / BatchNorm / ReLU after the last pool; an identity problem of the
+    first launch gives branch 0 its epilogue) instead of the 114-channel input; two launches of dilated 3x3 convolutions
+    (dilations 1 / 3 / 9 / 27 of all heads batched); then ONE chain launch (ojdf_conv_chain) runs the four 19 -> 114
+    branch-out convolutions and the `final` convolution: the concatenation becomes a sum over four 114-column slices of
+    `final`, the branch outputs live only in tensor memory; the global-pool branch is folded into the bias of `final`
+    (computed on a side stream);
+  * Pred (modules/model.py:24-52): all eleven 1x1 layers as ONE chain launch, ending in tanh * output_scale and writing
+    (N, n_points) f32 -- exactly the layout the integrator consumes, so no NCHW<->NHWC permutes exist anywhere.
+    OJDF_CHAIN=0 / net.use_chain = False: one launch per layer.
 
 Channel groups are padded to a multiple of 4 channels inside the buffers (19 -> 20, 114 -> 116): every
-concatenation offset is then 16-byte aligned, which is what the tensor-core kernel's TMA-store epilogue
+concatenation offset is then 16-byte aligned, which is what the kernels' TMA-store epilogue
 needs; the consumers' weights carry zero rows at the pad positions (`cin_map`).
 
 Only used in eval mode under torch.no_grad(); training (autograd through FusionNet, row a2) keeps
