@@ -87,3 +87,30 @@ def test_average_pools_commute_with_the_1x1_convolution():
     for _ in range(3):
         a, b = pool(a), pool(b)
         assert float((F.conv2d(a, w) - b).abs().max()) < 1e-13
+
+
+def test_merged_vortex_first_layer_and_final_slices():
+    """FusionNetEngine's host transforms of a VortexPooling block (modules/model.py:100-161): the merged first-layer image
+    holds branch b's 1x1 weights in output rows [20 b, 20 b + 19) (pad rows zero, input columns at their padded positions),
+    and the four `final` slices of the chain launch are the columns of the concatenated convolution in branch order."""
+    from online_joint_depthfusion_and_semantic_b200.modules.fusion_engine import _Vortex
+    from online_joint_depthfusion_and_semantic_b200.modules.model import VortexPooling
+    torch.manual_seed(3)
+    cin, mid, cout = 38, 19, 114
+    m = VortexPooling(cin, mid, cout, (6, 5)).eval()
+    pos, width = group_map(2, 19)                              # two 19-channel groups at pitch 20
+    v = _Vortex(m, 'cpu', (pos, width))
+    w_all = _unpack_tc(v.raw_all.weights_tc, width, 4 * 20, 1)[0]            # (80, 40)
+    for b, br in enumerate(m.branches):
+        wb = br[0].weight.detach().reshape(mid, cin)
+        assert torch.equal(w_all[20 * b:20 * b + mid][:, pos], wb)
+        assert float(w_all[20 * b + mid].abs().max()) == 0.0                  # pad row of the group
+    assert float(w_all[:, [19, 39]].abs().max()) == 0.0                       # pad input channels
+    wf = m.final[0].weight.detach().reshape(cout, 5 * cout)
+    for b in range(4):
+        fb = _unpack_tc(v.final_b[b].weights_tc, cout, cout, 1)[0]
+        assert torch.equal(fb, wf[:, cout * (1 + b):cout * (2 + b)])
+    # branch 0's deferred epilogue = its folded BatchNorm
+    bn = m.branches[0][1]
+    s = bn.weight.detach().double() / torch.sqrt(bn.running_var.double() + bn.eps)
+    assert torch.allclose(v.post[0][0][:mid].double(), s, rtol=1e-6)
