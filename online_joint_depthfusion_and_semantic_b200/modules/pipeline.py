@@ -257,7 +257,7 @@ class Pipeline(nn.Module):
             rays = self._extractor.rays(frame, batch['extrinsics'], batch['intrinsics'], volume['origin'], volume['resolution'])
             plan = self._integrator.plan(rays['ray'], filtered_frame, self.n_points, self.config.FUSION_MODEL.n_tail_points,
                                          volume['current'].shape)
-        scores, sem_ids = self._semantic_frame(batch, as_uint8=False)
+        scores, sem_ids = self._semantic_frame(batch, as_uint8=True)     # labels stay u8 end to end (no .long() / .type() round trip)
         pack = self._pack_target(frame, sem_ids) if frame.is_cuda else None
         values = self._extractor.forward(frame, batch['extrinsics'], batch['intrinsics'], volume['current'],
                                          volume['weights'], volume['origin'], volume['resolution'], rays=rays, pack=pack)
