@@ -125,6 +125,12 @@ __global__ void __launch_bounds__(kCThreads, 1) conv_chain_kernel(const __grid_c
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (threadIdx.x == 96)
+        for (int z = 0; z < prm.nz; ++z) {
+            for (int s = 0; s < prm.nsteps; ++s)
+                if (prm.st[s].src >= 0) prefetch_map(&prm.in_map[prm.st[s].src][z]);
+            if (prm.store_mode == 0) prefetch_map(&prm.out_map[z]);
+        }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -395,7 +401,9 @@ __global__ void __launch_bounds__(kCThreads, 1) conv_chain_kernel(const __grid_c
                 }
             }
         }
-        if (prm.store_mode == 0 && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        // the staging slabs must have been READ before the CTA (and its shared memory) goes away; the global writes of the
+        // bulk stores complete on their own before the grid does
+        if (prm.store_mode == 0 && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();

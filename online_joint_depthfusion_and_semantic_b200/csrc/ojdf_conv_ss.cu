@@ -224,6 +224,8 @@ __global__ void __launch_bounds__(kSsThreads, 1) conv_ss_kernel(const __grid_con
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (threadIdx.x == 32)
+        for (int i = 0; i < prm.nprob; ++i) { prefetch_map(&prm.in_map[i]); if (prm.store_mode == 0) prefetch_map(&prm.out_map[i]); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -532,7 +534,9 @@ __global__ void __launch_bounds__(kSsThreads, 1) conv_ss_kernel(const __grid_con
             mbar_arrive(acc_empty(buf));
             s += gr.n;
         }
-        if (prm.store_mode == 0 && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        // the staging slabs must have been READ before the CTA (and its shared memory) goes away; the global writes of the
+        // bulk stores complete on their own before the grid does
+        if (prm.store_mode == 0 && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     if (prof && lane == 0) {
         const int slot = warp == kProducerWarp ? 2 : warp == kIssuerWarp ? 6 : warp == kSplit0 ? 9 : 14;

@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(kWtThreads, 1) conv_wt_kernel(const __grid_con
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (threadIdx.x == 64)
+        for (int i = 0; i < prm.nprob; ++i) prefetch_map(&prm.in_map[i]);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
